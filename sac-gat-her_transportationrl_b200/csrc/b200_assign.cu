@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <string.h>
+#include <vector>
 
 namespace {
 
@@ -56,6 +57,9 @@ struct Params {
     const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
     const float *t0_csc, *cap0_csc, *t0, *cap0;
     const void *od_q;  // REAL
+    // small-network kernel only: TMA blob (node records + dense demand), per-slot link id / cost index
+    const unsigned char *small_blob;
+    const uint8_t *small_eid, *small_wpos;
     double total_demand;
     // batch
     int B, K, method, it0, ls_iters;
@@ -555,6 +559,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
     }
 }
 
+#include "b200_assign_small.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -567,6 +573,8 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.topo = g->topo; p.row = g->row; p.origins = g->origins; p.od_ptr = g->od_ptr; p.od_dst = g->od_dst;
     p.t0_csc = g->t0_csc; p.cap0_csc = g->cap0_csc; p.t0 = g->t0; p.cap0 = g->cap0;
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
+    p.small_blob = prec == B200_F32 ? g->small_blob32 : g->small_blob64;
+    p.small_eid = g->small_eid; p.small_wpos = g->small_wpos;
     p.total_demand = g->total_demand;
     p.B = B; p.alpha = alpha; p.beta = beta;
     return p;
@@ -590,6 +598,54 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p, 
 }
 
 }  // namespace
+
+// Small-network eligibility + static tables (called by b200_graph_create with the host CSC and
+// the OD list).  Builds one TMA-able blob per precision: node records | dense demand Q[node][slot].
+int b200_small_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src, const int32_t *in_eid,
+                       int num_od, const int32_t *od_o, const int32_t *od_d, const double *od_q,
+                       const int32_t *origin_slot)
+{
+    g->small_ok = 0;
+    const int N = g->N, E = g->E, O = g->O;
+    if (N > kSmallMaxN || E > kSmallMaxE || O > kSmallMaxO || O < 1 || g->max_in_deg > kSmallMaxD) return 0;
+    const int D = g->max_in_deg < 3 ? 3 : g->max_in_deg, DP = (D + 1) & ~1;
+    if (make_small_layout(N, E, O, D, 8).total > kSmemLimit) return 0;
+    std::vector<uint8_t> eid(E), wpos(E);
+    for (int prec = 0; prec < 2; ++prec) {
+        const int rb = prec == 0 ? 4 : 8;
+        const SmallLayout L = make_small_layout(N, E, O, D, rb);
+        std::vector<unsigned char> blob(L.blob_bytes, 0);
+        uint16_t *rec1 = (uint16_t *)blob.data();
+        uint8_t *rec2 = blob.data() + L.off_rec2;
+        memset(rec2, 255, (size_t)N * 16);
+        for (int v = 0; v < N; ++v) {
+            rec1[v * 8 + 0] = (uint16_t)(v * O * 8);
+            for (int j = 0; j < 7; ++j) rec1[v * 8 + 1 + j] = (uint16_t)(v * O * 8);  // padding: the node itself
+            for (int k = in_ptr[v], j = 0; k < in_ptr[v + 1]; ++k, ++j) {
+                rec1[v * 8 + 1 + j] = (uint16_t)(in_src[k] * O * 8);
+                rec2[v * 16 + j] = (uint8_t)in_src[k];
+                rec2[v * 16 + 8 + j] = (uint8_t)in_eid[k];
+                eid[k] = (uint8_t)in_eid[k];
+                wpos[k] = (uint8_t)(v * DP + j);
+            }
+        }
+        for (int k = 0; k < num_od; ++k) {
+            const size_t idx = (size_t)od_d[k] * O + origin_slot[od_o[k]];
+            if (prec == 0) ((float *)(blob.data() + L.off_q))[idx] += (float)od_q[k];
+            else ((double *)(blob.data() + L.off_q))[idx] += od_q[k];
+        }
+        unsigned char **dst = prec == 0 ? &g->small_blob32 : &g->small_blob64;
+        if (cudaMalloc((void **)dst, blob.size()) != cudaSuccess) return 0;
+        if (cudaMemcpy(*dst, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+    }
+    if (N * DP > 255) return 0;  // wpos is a byte
+    if (cudaMalloc((void **)&g->small_eid, E) != cudaSuccess || cudaMalloc((void **)&g->small_wpos, E) != cudaSuccess) return 0;
+    cudaMemcpy(g->small_eid, eid.data(), E, cudaMemcpyHostToDevice);
+    cudaMemcpy(g->small_wpos, wpos.data(), E, cudaMemcpyHostToDevice);
+    g->small_D = D;
+    g->small_ok = 1;
+    return 1;
+}
 
 // Warps per CTA: enough to spread the origins evenly, bounded by shared memory.
 int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
@@ -686,8 +742,15 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
     Params p = base_params(g, B, prec, alpha, beta);
     p.K = K; p.method = method; p.dmg = dmg; p.active = active; p.flow = flow; p.dprev = dprev; p.tstt = tstt; p.gap = gap;
     p.unassigned = unassigned; p.status = status; p.penalty = penalty; p.ls_iters = ls_iters;
-    int rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream)
+    int rc;
+    if (g->small_ok && !g->force_general) {
+        // Sioux-Falls class: one warp per scenario, lane = origin
+        rc = prec == B200_F32 ? launch_small<float>(g, p, (cudaStream_t)stream)
+                              : launch_small<double>(g, p, (cudaStream_t)stream);
+    } else {
+        rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream)
                               : launch_cta_kernel(assign_fused_kernel<double>, g, prec, p, (cudaStream_t)stream);
+    }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;
     return rc;
 }

@@ -66,6 +66,12 @@ struct b200_graph {
     size_t smem_f32, smem_f64;
     int warps_f32, warps_f64;
     int32_t *origins_host;
+    // small-network kernel (b200_assign_small.cuh): per-precision TMA blob (node records + dense
+    // demand), per-CSC-slot link id / padded cost index; force_general = 1 routes b200_assign
+    // through the general kernel (test hook, env B200_FORCE_GENERAL)
+    unsigned char *small_blob32, *small_blob64;
+    uint8_t *small_eid, *small_wpos;
+    int small_ok, small_D, force_general;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -353,3 +353,22 @@ def test_line_search_beats_fixed_step_gap(b200env, native_lib, sf_graph, sf_orac
         o = sf_oracle.assign(masks[b], None, 30, "fw_ls", dtype=np.float64)
         np.testing.assert_allclose(ls["flow"][b], o["flow"], rtol=1e-6, atol=1e-3)
         np.testing.assert_allclose(ls["tstt"][b], o["tstt"], rtol=1e-7)
+
+
+def test_general_and_small_network_kernels_agree(b200env, native_lib, sf_graph, sf_oracle, golden, monkeypatch):
+    """Sioux Falls qualifies for the lane-per-origin kernel; B200_FORCE_GENERAL routes the same
+    network through the general CTA-per-scenario kernel.  Both must equal the oracle bit for bit."""
+    G = golden("sf_batch4096_fw_k20.npz")
+    masks = _masks_from_idx(G["dmg"][:96], 76)
+    monkeypatch.setenv("B200_FORCE_GENERAL", "1")
+    eng_general = _engine(b200env, sf_graph, "fp32")
+    monkeypatch.delenv("B200_FORCE_GENERAL")
+    eng_small = _engine(b200env, sf_graph, "fp32")
+    for method in ("fw", "msa"):
+        a = _assign(eng_general, masks, 20, method)
+        b = _assign(eng_small, masks, 20, method)
+        assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["tstt"], b["tstt"])
+        np.testing.assert_allclose(a["gap"], b["gap"], rtol=1e-9)
+        for s in (0, 50, 95):
+            o = sf_oracle.assign(masks[s], None, 20, method)
+            assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"]
