@@ -13,7 +13,7 @@ from typing import List
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libb200assign.so")
+LIB_PATH = os.environ.get("B200_LIB", os.path.join(PKG_DIR, "libb200assign.so"))  # env override: kernel A/B runs
 SOURCES = ["b200_graph.cu", "b200_assign.cu", "b200_env.cu", "b200_gat.cu"]
 HEADERS = ["b200_common.cuh", os.path.join("..", "..", "include", "b200_assign.h")]
 

@@ -69,9 +69,9 @@ struct b200_graph {
     // small-network kernel (b200_assign_small.cuh): per-precision TMA blob (node records + dense
     // demand), per-CSC-slot link id / padded cost index; force_general = 1 routes b200_assign
     // through the general kernel (test hook, env B200_FORCE_GENERAL)
-    unsigned char *small_blob32, *small_blob64;
+    unsigned char *small_blob32, *small_blob64, *small_blob_i32;
     uint8_t *small_eid, *small_wpos;
-    int small_ok, small_D, force_general;
+    int small_ok, small_D, small_intq, force_general;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,5 @@
+import sys,json
+for l in sys.stdin:
+    if l.startswith("{"):
+        d=json.loads(l); print("value %.0f  ms/step %.3f  e2e %.0f  frac %.4f"%(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"]))
+    else: print(l.rstrip())

@@ -372,3 +372,23 @@ def test_general_and_small_network_kernels_agree(b200env, native_lib, sf_graph, 
         for s in (0, 50, 95):
             o = sf_oracle.assign(masks[s], None, 20, method)
             assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"]
+
+
+def test_fractional_demand_uses_float_scatter_add(b200env, native_lib, sf_graph):
+    """Non-integer demands take the float scatter-add path of the small-network kernel (integer
+    demands take the exact int32 redux path); sums are then order-dependent -> tolerance parity."""
+    from oracle.c_oracle import COracle
+    g = b200env.GraphData(num_nodes=24, edges=sf_graph.edges,
+                          od_demand={k: q * 0.37 + 0.123 for k, q in sf_graph.od_demand.items()})
+    orc = COracle.from_graph_data(g)
+    rng = np.random.default_rng(11)
+    masks = np.zeros((8, 76), np.uint8)
+    for b in range(8):
+        masks[b, rng.choice(76, 22, replace=False)] = 1
+    for precision, dtype, rtol in (("fp32", np.float32, 2e-5), ("fp64", np.float64, 1e-10)):
+        eng = _engine(b200env, g, precision)
+        out = _assign(eng, masks, 20, "fw")
+        for b in range(8):
+            o = orc.assign(masks[b], None, 20, "fw", dtype=dtype)
+            np.testing.assert_allclose(out["flow"][b], o["flow"], rtol=rtol, atol=rtol * 10)
+            assert abs(out["tstt"][b] - o["tstt"]) / o["tstt"] <= rtol
