@@ -14,8 +14,10 @@ from typing import List
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("B200_LIB", os.path.join(PKG_DIR, "libb200assign.so"))  # env override: kernel A/B runs
-SOURCES = ["b200_graph.cu", "b200_assign.cu", "b200_env.cu", "b200_gat.cu"]
-HEADERS = ["b200_common.cuh", os.path.join("..", "..", "include", "b200_assign.h")]
+SOURCES = ["b200_graph.cu", "b200_assign.cu", "b200_assign_small.cu", "b200_assign_static.cu", "b200_env.cu",
+           "b200_gat.cu"]
+HEADERS = ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", "b200_assign_static.cuh", "b200_topo_siouxfalls.h",
+           os.path.join("..", "..", "include", "b200_assign.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,17 +54,43 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
+def _obj_path(src: str) -> str:
+    return os.path.join(CSRC, "_obj", os.path.splitext(src)[0] + ".o")
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into libb200assign.so (sm_100a).  nvcc cross-compiles without a GPU."""
+    """Compile csrc/*.cu into libb200assign.so (sm_100a).  nvcc cross-compiles without a GPU.
+    One object per source, compiled in parallel, then linked; objects live in csrc/_obj/."""
     if not force and not _stale():
         return LIB_PATH
-    cmd: List[str] = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
-    cmd += ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(os.path.join(CSRC, "_obj"), exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    api = os.path.join("..", "..", "include", "b200_assign.h")
+    deps = {"b200_assign.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
+            "b200_assign_small.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", api],
+            "b200_assign_static.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_static.cuh",
+                                      "b200_topo_siouxfalls.h", api]}
+    procs = []
+    for src in SOURCES:
+        obj, path = _obj_path(src), os.path.join(CSRC, src)
+        hdr_time = max(os.path.getmtime(os.path.normpath(os.path.join(CSRC, h)))
+                       for h in deps.get(src, ["b200_common.cuh", api]))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_time):
+            continue
+        procs.append((src, subprocess.Popen([_nvcc()] + compile_flags + ["-c", "-o", obj, path],
+                                            stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    log = []
+    for src, proc in procs:
+        _out, err = proc.communicate()
+        log.append(err)
+        if proc.returncode != 0:
+            raise NativeLibraryError(f"nvcc failed on {src}:\n" + err[-4000:])
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB_PATH] + [_obj_path(s) for s in SOURCES],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise NativeLibraryError("nvcc failed:\n" + res.stderr[-4000:])
+        raise NativeLibraryError("link failed:\n" + res.stderr[-4000:])
     if verbose:
-        print(res.stderr)
+        print("\n".join(log))
     return LIB_PATH
 
 

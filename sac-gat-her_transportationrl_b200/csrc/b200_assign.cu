@@ -17,78 +17,11 @@
 // unique fixed point dist[v] = min_u fl(dist[u] + w(u,v)) - the same values Dijkstra produces for
 // positive costs, so predecessor selection "tight in-link with the smallest dist[u], then the
 // largest u" reproduces scipy's trees bit for bit.
-#include "b200_common.cuh"
+#include "b200_assign_internal.cuh"
 
-#include <algorithm>
-#include <math.h>
-#include <string.h>
-#include <type_traits>
-#include <vector>
+using namespace b200i;
 
 namespace {
-
-constexpr int kMaxWarps = 16;
-constexpr int kMinWarps = 2;
-constexpr size_t kSmemLimit = 227 * 1024;
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
-
-struct SmemLayout {
-    size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
-};
-
-__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_ints, int warps, int real_bytes)
-{
-    SmemLayout L;
-    size_t o = 0;
-    L.off_bar = o;  o += 16;
-    L.off_topo = o; o += align16((size_t)topo_ints * 4);
-    L.off_w = o;    o += align16((size_t)E * 8);
-    L.off_aux = o;  o += align16((size_t)E * real_bytes);
-    L.off_flow = o; o += align16((size_t)E * real_bytes);
-    L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
-    L.off_warp = o;
-    L.warp_stride = align16((size_t)N * 8) + align16((size_t)N * 4);
-    L.total = o + L.warp_stride * warps;
-    return L;
-}
-
-// shared-memory layout of the small-network kernel, computed on the host (b200_assign_small.cuh)
-struct SmallOffsets {
-    int blob_bytes, off_rec2, off_q, off_dist, off_sacc, off_cnt, off_stk, off_pu, off_pe, off_w, off_aux, off_flow,
-        warp_stride;
-};
-
-struct Params {
-    SmallOffsets so;
-    // static network
-    int N, E, O, topo_ints, off_in_src, off_in_eid;
-    const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
-    const float *t0_csc, *cap0_csc, *t0, *cap0;
-    const void *od_q;  // REAL
-    // small-network kernel only: TMA blob (node records + dense demand), per-slot link id / cost index
-    const unsigned char *small_blob;
-    const uint8_t *small_eid, *small_wpos;
-    double total_demand;
-    // batch
-    int B, K, method, it0, ls_iters;
-    const uint8_t *dmg, *active;
-    void *flow, *dprev, *t, *aux;          // real [B][E]
-    double *tstt, *gap, *unassigned;       // [B]
-    const double *unassigned_in;
-    int32_t *status;
-    double *dist_out;                      // [B][O][N]
-    int32_t *pred_out, *pedge_out;
-    const int32_t *pedge_in;
-    double alpha, beta, penalty;
-};
-
-template <typename REAL> __device__ __forceinline__ REAL rmul(REAL a, REAL b);
-template <> __device__ __forceinline__ float rmul<float>(float a, float b) { return __fmul_rn(a, b); }
-template <> __device__ __forceinline__ double rmul<double>(double a, double b) { return __dmul_rn(a, b); }
-template <typename REAL> __device__ __forceinline__ REAL radd(REAL a, REAL b);
-template <> __device__ __forceinline__ float radd<float>(float a, float b) { return __fadd_rn(a, b); }
-template <> __device__ __forceinline__ double radd<double>(double a, double b) { return __dadd_rn(a, b); }
 
 // Everything a CTA needs, carved out of dynamic shared memory.
 template <typename REAL>
@@ -156,14 +89,6 @@ struct Cta {
 // ---------------------------------------------------------------------------------------------
 // S1: link costs of the CTA's flow vector into w[] (CSC-slot order, as double)
 // ---------------------------------------------------------------------------------------------
-template <typename REAL>
-__device__ __forceinline__ REAL link_cost(const Params &p, int k, REAL f, bool damaged)
-{
-    if (damaged) return (REAL)1e6;
-    return Bpr<REAL>::eval(f, (REAL)__ldg(p.cap0_csc + k), (REAL)__ldg(p.t0_csc + k), (REAL)p.alpha, (REAL)p.beta,
-                           p.beta == 4.0);
-}
-
 template <typename REAL>
 __device__ void cta_costs_from_flow(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b)
 {
@@ -250,34 +175,6 @@ __device__ double warp_aon_walk(Cta<REAL> &c, const Params &p, int slot, int ori
         }
     }
     return un;
-}
-
-// numpy's pairwise summation order (np.sum of a contiguous fp array, reference :727), evaluated
-// cooperatively by one warp: lanes j, j+8, .. replicate the 8 running sums of a <=128 block.
-template <typename REAL>
-__device__ REAL warp_pairwise(const REAL *a, int n)
-{
-    const int lane = threadIdx.x & 31;
-    if (n < 8) {
-        REAL r = 0;
-        for (int i = 0; i < n; ++i) r = radd<REAL>(r, a[i]);
-        return r;
-    }
-    if (n <= 128) {
-        const int j = lane & 7, lim = n - (n % 8);
-        REAL r = a[j];
-        for (int i = 8; i < lim; i += 8) r = radd<REAL>(r, a[i + j]);
-        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 1));
-        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 2));
-        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        for (int i = lim; i < n; ++i) r = radd<REAL>(r, a[i]);
-        return r;
-    }
-    int n2 = n / 2;
-    n2 -= n2 % 8;
-    const REAL lo = warp_pairwise<REAL>(a, n2);
-    const REAL hi = warp_pairwise<REAL>(a + n2, n - n2);
-    return radd<REAL>(lo, hi);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -568,7 +465,6 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
     }
 }
 
-#include "b200_assign_small.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // host side
@@ -584,6 +480,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
     p.small_blob = g->small_intq ? g->small_blob_i32 : (prec == B200_F32 ? g->small_blob32 : g->small_blob64);
     p.small_eid = g->small_eid; p.small_wpos = g->small_wpos;
+    p.st_t0 = g->st_t0; p.st_cap0 = g->st_cap0; p.st_eid = g->st_eid; p.st_origpos = g->st_origpos;
     p.total_demand = g->total_demand;
     p.B = B; p.alpha = alpha; p.beta = beta;
     return p;
@@ -607,133 +504,6 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p, 
 }
 
 }  // namespace
-
-// Sweep order for the small-network kernel: Gauss-Seidel converges fastest when the node order
-// follows the direction paths travel.  Candidates: nodes sorted by free-flow distance from a root,
-// for every root; the winner needs the fewest alternating sweeps on the free-flow costs with a
-// few deterministic damage patterns (all origins at once, exactly what the kernel does).
-static std::vector<int> small_sweep_order(int N, int E, const int32_t *in_ptr, const int32_t *in_src,
-                                          const int32_t *in_eid, const float *t0, const int32_t *origins, int O)
-{
-    auto count_sweeps = [&](const std::vector<int> &order, const std::vector<double> &w) {
-        std::vector<double> d((size_t)O * N, INFINITY);
-        for (int s = 0; s < O; ++s) d[(size_t)s * N + origins[s]] = 0.0;
-        int sweeps = 0;
-        for (;; ++sweeps) {
-            bool changed = false;
-            for (int n = 0; n < N; ++n) {
-                const int v = order[(sweeps & 1) ? N - 1 - n : n];
-                for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k)
-                    for (int s = 0; s < O; ++s) {
-                        const double c = d[(size_t)s * N + in_src[k]] + w[k];
-                        if (c < d[(size_t)s * N + v]) { d[(size_t)s * N + v] = c; changed = true; }
-                    }
-            }
-            if (!changed || sweeps > 4 * N) break;
-        }
-        return sweeps + 1;
-    };
-    std::vector<std::vector<double>> patterns;
-    unsigned long long lcg = 0x9E3779B97F4A7C15ull;
-    for (int pat = 0; pat < 6; ++pat) {
-        std::vector<double> w(E);
-        for (int k = 0; k < E; ++k) {
-            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
-            const bool dmg = pat > 0 && ((lcg >> 33) % 10) < 3;
-            lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
-            const double jitter = 1.0 + 0.5 * (double)((lcg >> 33) % 1000) / 1000.0;
-            w[k] = dmg ? 1e6 : (double)t0[in_eid[k]] * (pat > 0 ? jitter : 1.0);
-        }
-        patterns.push_back(w);
-    }
-    std::vector<int> best_order(N);
-    for (int v = 0; v < N; ++v) best_order[v] = v;
-    long best_cost = 0;
-    for (auto &w : patterns) best_cost += count_sweeps(best_order, w);
-    for (int root = 0; root < N; ++root) {
-        // undirected free-flow distances from root (O(N^2) Dijkstra), order = ascending distance
-        std::vector<double> dist(N, INFINITY);
-        std::vector<char> done(N, 0);
-        dist[root] = 0.0;
-        for (int it = 0; it < N; ++it) {
-            int u = -1;
-            for (int v = 0; v < N; ++v) if (!done[v] && (u < 0 || dist[v] < dist[u])) u = v;
-            if (u < 0) break;
-            done[u] = 1;
-            for (int v = 0; v < N; ++v)
-                for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k) {
-                    const int a = in_src[k];
-                    const double wk = (double)t0[in_eid[k]];
-                    if (a == u && dist[u] + wk < dist[v]) dist[v] = dist[u] + wk;
-                    if (v == u && dist[u] + wk < dist[a]) dist[a] = dist[u] + wk;
-                }
-        }
-        std::vector<int> order(N);
-        for (int v = 0; v < N; ++v) order[v] = v;
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return dist[a] < dist[b]; });
-        long cost = 0;
-        for (auto &w : patterns) cost += count_sweeps(order, w);
-        if (cost < best_cost) { best_cost = cost; best_order = order; }
-    }
-    return best_order;
-}
-
-// Small-network eligibility + static tables (called by b200_graph_create with the host CSC and
-// the OD list).  Builds TMA-able blobs: node records in sweep order | dense demand Q[node][slot]
-// as float, double and (when every demand is an integer) int32.
-int b200_small_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src, const int32_t *in_eid,
-                       const float *t0, int num_od, const int32_t *od_o, const int32_t *od_d, const double *od_q,
-                       const int32_t *origin_slot)
-{
-    g->small_ok = 0;
-    const int N = g->N, E = g->E, O = g->O;
-    if (N > kSmallMaxN || E > kSmallMaxE || O > kSmallMaxO || O < 1 || g->max_in_deg > kSmallMaxD) return 0;
-    const int D = g->max_in_deg < 3 ? 3 : g->max_in_deg, DP = (D + 1) & ~1;
-    if (N * DP > 255) return 0;  // padded cost index is a byte
-    if (make_small_layout(N, E, O, D, 8, 8).total > kSmemLimit) return 0;
-    bool intq = g->total_demand < 16777216.0;  // 2^24: fp32 link sums stay exact
-    for (int k = 0; k < num_od && intq; ++k) intq = od_q[k] >= 0.0 && od_q[k] == floor(od_q[k]);
-    const std::vector<int> order = small_sweep_order(N, E, in_ptr, in_src, in_eid, t0, g->origins_host, O);
-    std::vector<uint8_t> eid(E), wpos(E);
-    for (int variant = 0; variant < 3; ++variant) {   // 0 float Q, 1 double Q, 2 int32 Q
-        if (variant == 2 && !intq) break;
-        const int qb = variant == 1 ? 8 : 4;
-        const SmallLayout L = make_small_layout(N, E, O, D, qb, qb);
-        std::vector<unsigned char> blob(L.blob_bytes, 0);
-        uint16_t *rec1 = (uint16_t *)blob.data();
-        uint8_t *rec2 = blob.data() + L.off_rec2;
-        memset(rec2, 255, (size_t)N * 16);
-        for (int i = 0; i < N; ++i) {
-            const int v = order[i], deg = in_ptr[v + 1] - in_ptr[v];
-            rec1[i * 8 + 0] = (uint16_t)(v * O * 8) | (uint16_t)(deg > 3 ? 0x8000 : 0);
-            for (int j = 0; j < 7; ++j) rec1[i * 8 + 1 + j] = (uint16_t)(v * O * 8);  // padding: the node itself
-            rec2[i * 16 + 7] = (uint8_t)v;
-            for (int k = in_ptr[v], j = 0; k < in_ptr[v + 1]; ++k, ++j) {
-                rec1[i * 8 + 1 + j] = (uint16_t)(in_src[k] * O * 8);
-                rec2[i * 16 + j] = (uint8_t)in_src[k];
-                rec2[i * 16 + 8 + j] = (uint8_t)in_eid[k];
-                eid[k] = (uint8_t)in_eid[k];
-                wpos[k] = (uint8_t)(i * DP + j);
-            }
-        }
-        for (int k = 0; k < num_od; ++k) {
-            const size_t idx = (size_t)od_d[k] * O + origin_slot[od_o[k]];
-            if (variant == 0) ((float *)(blob.data() + L.off_q))[idx] += (float)od_q[k];
-            else if (variant == 1) ((double *)(blob.data() + L.off_q))[idx] += od_q[k];
-            else ((int32_t *)(blob.data() + L.off_q))[idx] += (int32_t)od_q[k];
-        }
-        unsigned char **dst = variant == 0 ? &g->small_blob32 : variant == 1 ? &g->small_blob64 : &g->small_blob_i32;
-        if (cudaMalloc((void **)dst, blob.size()) != cudaSuccess) return 0;
-        if (cudaMemcpy(*dst, blob.data(), blob.size(), cudaMemcpyHostToDevice) != cudaSuccess) return 0;
-    }
-    if (cudaMalloc((void **)&g->small_eid, E) != cudaSuccess || cudaMalloc((void **)&g->small_wpos, E) != cudaSuccess) return 0;
-    cudaMemcpy(g->small_eid, eid.data(), E, cudaMemcpyHostToDevice);
-    cudaMemcpy(g->small_wpos, wpos.data(), E, cudaMemcpyHostToDevice);
-    g->small_D = D;
-    g->small_intq = intq ? 1 : 0;
-    g->small_ok = 1;
-    return 1;
-}
 
 // Warps per CTA: enough to spread the origins evenly, bounded by shared memory.
 int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
@@ -831,10 +601,12 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
     p.K = K; p.method = method; p.dmg = dmg; p.active = active; p.flow = flow; p.dprev = dprev; p.tstt = tstt; p.gap = gap;
     p.unassigned = unassigned; p.status = status; p.penalty = penalty; p.ls_iters = ls_iters;
     int rc;
-    if (g->small_ok && !g->force_general) {
+    if (g->static_ok && !g->force_general && !g->force_small) {
+        // compiled-in topology (Sioux Falls): straight-line lane-per-origin kernel
+        rc = b200_launch_static(g, p, prec, (cudaStream_t)stream);
+    } else if (g->small_ok && !g->force_general) {
         // Sioux-Falls class: one warp per scenario, lane = origin
-        rc = prec == B200_F32 ? launch_small<float>(g, p, (cudaStream_t)stream)
-                              : launch_small<double>(g, p, (cudaStream_t)stream);
+        rc = b200_launch_small(g, p, prec, (cudaStream_t)stream);
     } else {
         rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream)
                               : launch_cta_kernel(assign_fused_kernel<double>, g, prec, p, (cudaStream_t)stream);

@@ -1,0 +1,125 @@
+// Internals shared by the assignment translation units (b200_assign.cu: stage kernels, general
+// fused kernel, C ABI; b200_assign_small.cu: generic lane-per-origin kernel; b200_assign_static.cu:
+// network-specialised kernel).  Everything here is inline / template code.
+#pragma once
+#include "b200_common.cuh"
+
+#include <algorithm>
+#include <math.h>
+#include <string.h>
+#include <type_traits>
+#include <vector>
+
+namespace b200i {
+
+
+constexpr int kMaxWarps = 16;
+constexpr int kMinWarps = 2;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+struct SmemLayout {
+    size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
+};
+
+__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_ints, int warps, int real_bytes)
+{
+    SmemLayout L;
+    size_t o = 0;
+    L.off_bar = o;  o += 16;
+    L.off_topo = o; o += align16((size_t)topo_ints * 4);
+    L.off_w = o;    o += align16((size_t)E * 8);
+    L.off_aux = o;  o += align16((size_t)E * real_bytes);
+    L.off_flow = o; o += align16((size_t)E * real_bytes);
+    L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
+    L.off_warp = o;
+    L.warp_stride = align16((size_t)N * 8) + align16((size_t)N * 4);
+    L.total = o + L.warp_stride * warps;
+    return L;
+}
+
+// shared-memory layout of the small-network kernel, computed on the host (b200_assign_small.cuh)
+struct SmallOffsets {
+    int blob_bytes, off_rec2, off_q, off_dist, off_sacc, off_cnt, off_stk, off_pu, off_pe, off_w, off_aux, off_flow,
+        warp_stride;
+};
+
+struct Params {
+    SmallOffsets so;
+    // static network
+    int N, E, O, topo_ints, off_in_src, off_in_eid;
+    const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
+    const float *t0_csc, *cap0_csc, *t0, *cap0;
+    const void *od_q;  // REAL
+    // small-network kernel only: TMA blob (node records + dense demand), per-slot link id / cost index
+    const unsigned char *small_blob;
+    const uint8_t *small_eid, *small_wpos;
+    // network-specialised kernel only: demand blob, per-slot t0 / cap0 / link id, origin positions
+    const unsigned char *st_blob;
+    const float *st_t0, *st_cap0;
+    const uint8_t *st_eid;
+    const int32_t *st_origpos;
+    double total_demand;
+    // batch
+    int B, K, method, it0, ls_iters;
+    const uint8_t *dmg, *active;
+    void *flow, *dprev, *t, *aux;          // real [B][E]
+    double *tstt, *gap, *unassigned;       // [B]
+    const double *unassigned_in;
+    int32_t *status;
+    double *dist_out;                      // [B][O][N]
+    int32_t *pred_out, *pedge_out;
+    const int32_t *pedge_in;
+    double alpha, beta, penalty;
+};
+
+template <typename REAL> __device__ __forceinline__ REAL rmul(REAL a, REAL b);
+template <> __device__ __forceinline__ float rmul<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double rmul<double>(double a, double b) { return __dmul_rn(a, b); }
+template <typename REAL> __device__ __forceinline__ REAL radd(REAL a, REAL b);
+template <> __device__ __forceinline__ float radd<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double radd<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <typename REAL>
+__device__ __forceinline__ REAL link_cost(const Params &p, int k, REAL f, bool damaged)
+{
+    if (damaged) return (REAL)1e6;
+    return Bpr<REAL>::eval(f, (REAL)__ldg(p.cap0_csc + k), (REAL)__ldg(p.t0_csc + k), (REAL)p.alpha, (REAL)p.beta,
+                           p.beta == 4.0);
+}
+
+// numpy's pairwise summation order (np.sum of a contiguous fp array, reference :727), evaluated
+// cooperatively by one warp: lanes j, j+8, .. replicate the 8 running sums of a <=128 block.
+template <typename REAL>
+__device__ REAL warp_pairwise(const REAL *a, int n)
+{
+    const int lane = threadIdx.x & 31;
+    if (n < 8) {
+        REAL r = 0;
+        for (int i = 0; i < n; ++i) r = radd<REAL>(r, a[i]);
+        return r;
+    }
+    if (n <= 128) {
+        const int j = lane & 7, lim = n - (n % 8);
+        REAL r = a[j];
+        for (int i = 8; i < lim; i += 8) r = radd<REAL>(r, a[i + j]);
+        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = radd<REAL>(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        for (int i = lim; i < n; ++i) r = radd<REAL>(r, a[i]);
+        return r;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const REAL lo = warp_pairwise<REAL>(a, n2);
+    const REAL hi = warp_pairwise<REAL>(a + n2, n - n2);
+    return radd<REAL>(lo, hi);
+}
+
+
+}  // namespace b200i
+
+// launchers implemented in the other translation units
+int b200_launch_small(const b200_graph *g, const b200i::Params &p, int prec, cudaStream_t st);
+int b200_launch_static(const b200_graph *g, const b200i::Params &p, int prec, cudaStream_t st);

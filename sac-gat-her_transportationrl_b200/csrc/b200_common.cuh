@@ -72,6 +72,15 @@ struct b200_graph {
     unsigned char *small_blob32, *small_blob64, *small_blob_i32;
     uint8_t *small_eid, *small_wpos;
     int small_ok, small_D, small_intq, force_general;
+    // network-specialised kernel (b200_assign_static.cuh): set when the link list equals a compiled-in
+    // topology header; per-CSC-slot t0 / cap0 / link id in the header's slot order, internal origin
+    // positions, dense demand Q[internal node][32 lanes].  force_small = 1 (env B200_FORCE_SMALL)
+    // routes b200_assign through the generic lane-per-origin kernel instead (test hook)
+    int static_ok, st_intq, force_small;
+    float *st_t0, *st_cap0;
+    uint8_t *st_eid;
+    int32_t *st_origpos;
+    unsigned char *st_blob32, *st_blob64, *st_blob_i32;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -37,6 +37,9 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out);   // b200_
 int b200_small_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src, const int32_t *in_eid,
                        const float *t0, int num_od, const int32_t *od_o, const int32_t *od_d, const double *od_q,
                        const int32_t *origin_slot);
+int b200_static_prepare(b200_graph *g, const int32_t *row, const int32_t *col, const float *t0, const float *cap0,
+                        int num_od, const int32_t *od_o, const int32_t *od_d, const double *od_q,
+                        const int32_t *origin_slot);
 
 extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, const int32_t *col, const float *t0,
                                  const float *cap0, int num_od, const int32_t *od_o, const int32_t *od_d,
@@ -118,6 +121,7 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     // test hook: route b200_assign through the general (CTA-per-scenario) kernel even when the
     // network qualifies for the small-network kernel
     g->force_general = getenv("B200_FORCE_GENERAL") != nullptr;
+    g->force_small = getenv("B200_FORCE_SMALL") != nullptr;
     g->N = N; g->E = E; g->O = O; g->num_od = num_od; g->max_in_deg = max_in; g->total_demand = total;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -150,6 +154,7 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     g->origins_host = (int32_t *)malloc(sizeof(int32_t) * std::max(O, 1));
     std::copy(origins.begin(), origins.end(), g->origins_host);
     b200_small_prepare(g, in_ptr.data(), in_src.data(), in_eid.data(), t0, num_od, od_o, od_d, od_q, origin_slot.data());
+    b200_static_prepare(g, row, col, t0, cap0, num_od, od_o, od_d, od_q, origin_slot.data());
     g->warps_f32 = b200_pick_warps(g, B200_F32, &g->smem_f32);
     g->warps_f64 = b200_pick_warps(g, B200_F64, &g->smem_f64);
     if (g->warps_f32 <= 0 || g->warps_f64 <= 0) {
@@ -167,7 +172,8 @@ extern "C" int b200_graph_destroy(b200_graph *g)
     cudaSetDevice(g->device);
     void *ptrs[] = {g->topo, g->row, g->col, g->t0, g->cap0, g->t0_csc, g->cap0_csc, g->origins, g->origin_slot,
                     g->od_ptr, g->od_dst, g->od_q64, g->od_q32, g->out_ptr, g->out_dst, g->out_eid,
-                    g->small_blob32, g->small_blob64, g->small_blob_i32, g->small_eid, g->small_wpos};
+                    g->small_blob32, g->small_blob64, g->small_blob_i32, g->small_eid, g->small_wpos,
+                    g->st_t0, g->st_cap0, g->st_eid, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(g->origins_host);
