@@ -355,23 +355,40 @@ def test_line_search_beats_fixed_step_gap(b200env, native_lib, sf_graph, sf_orac
         np.testing.assert_allclose(ls["tstt"][b], o["tstt"], rtol=1e-7)
 
 
-def test_general_and_small_network_kernels_agree(b200env, native_lib, sf_graph, sf_oracle, golden, monkeypatch):
-    """Sioux Falls qualifies for the lane-per-origin kernel; B200_FORCE_GENERAL routes the same
-    network through the general CTA-per-scenario kernel.  Both must equal the oracle bit for bit."""
+def test_general_small_and_static_kernels_agree(b200env, native_lib, sf_graph, sf_oracle, golden, monkeypatch):
+    """Sioux Falls takes the network-specialised (compile-time topology) kernel by default;
+    B200_FORCE_SMALL routes it through the generic lane-per-origin kernel and B200_FORCE_GENERAL
+    through the CTA-per-scenario kernel.  All three must equal the oracle bit for bit."""
     G = golden("sf_batch4096_fw_k20.npz")
     masks = _masks_from_idx(G["dmg"][:96], 76)
     monkeypatch.setenv("B200_FORCE_GENERAL", "1")
     eng_general = _engine(b200env, sf_graph, "fp32")
     monkeypatch.delenv("B200_FORCE_GENERAL")
+    monkeypatch.setenv("B200_FORCE_SMALL", "1")
     eng_small = _engine(b200env, sf_graph, "fp32")
+    eng_small64 = _engine(b200env, sf_graph, "fp64")
+    monkeypatch.delenv("B200_FORCE_SMALL")
+    eng_static = _engine(b200env, sf_graph, "fp32")
+    eng_static64 = _engine(b200env, sf_graph, "fp64")
     for method in ("fw", "msa"):
         a = _assign(eng_general, masks, 20, method)
         b = _assign(eng_small, masks, 20, method)
-        assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["tstt"], b["tstt"])
-        np.testing.assert_allclose(a["gap"], b["gap"], rtol=1e-9)
+        c = _assign(eng_static, masks, 20, method)
+        for x in (b, c):
+            assert np.array_equal(a["flow"], x["flow"]) and np.array_equal(a["tstt"], x["tstt"])
+            assert np.array_equal(a["status"], x["status"]) and np.array_equal(a["unassigned"], x["unassigned"])
+            np.testing.assert_allclose(a["gap"], x["gap"], rtol=1e-9)
         for s in (0, 50, 95):
             o = sf_oracle.assign(masks[s], None, 20, method)
             assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"]
+        b64, c64 = _assign(eng_small64, masks, 20, method), _assign(eng_static64, masks, 20, method)
+        assert np.array_equal(b64["flow"], c64["flow"]) and np.array_equal(b64["tstt"], c64["tstt"])
+    # cfw and the line-search extension: dot products are summed in a different link order
+    for method, rtol in (("cfw", 1e-5), ("fw_ls", 1e-6)):
+        b = _assign(eng_small64, masks[:16], 20, method)
+        c = _assign(eng_static64, masks[:16], 20, method)
+        np.testing.assert_allclose(c["flow"], b["flow"], rtol=rtol, atol=1e-6)
+        np.testing.assert_allclose(c["tstt"], b["tstt"], rtol=rtol)
 
 
 def test_fractional_demand_uses_float_scatter_add(b200env, native_lib, sf_graph):
