@@ -65,6 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     os.makedirs(os.path.join(CSRC, "_obj"), exist_ok=True)
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    compile_flags += os.environ.get("B200_NVCC_EXTRA", "").split()  # kernel-tuning experiments (-DB200_STATIC_MINB=..)
     api = os.path.join("..", "..", "include", "b200_assign.h")
     deps = {"b200_assign.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
             "b200_assign_small.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", api],

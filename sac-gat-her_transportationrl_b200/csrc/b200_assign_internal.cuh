@@ -58,7 +58,7 @@ struct Params {
     // network-specialised kernel only: demand blob, per-slot t0 / cap0 / link id, origin positions
     const unsigned char *st_blob;
     const float *st_t0, *st_cap0;
-    const uint8_t *st_eid;
+    const uint8_t *st_eid, *st_wpos;
     const int32_t *st_origpos;
     double total_demand;
     // batch

@@ -78,7 +78,7 @@ struct b200_graph {
     // routes b200_assign through the generic lane-per-origin kernel instead (test hook)
     int static_ok, st_intq, force_small;
     float *st_t0, *st_cap0;
-    uint8_t *st_eid;
+    uint8_t *st_eid, *st_wpos;
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32;
 };
