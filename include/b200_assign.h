@@ -96,6 +96,9 @@ int b200_assign(const b200_graph *g, int B, int prec, int K, int method, const u
 
 /* How many kernels the last b200_assign on this handle launched (for bench.py's gpu_launches). */
 int b200_assign_launches(const b200_graph *g);
+/* Which fused kernel b200_assign dispatches to for this network ("assign_static_kernel",
+ * "assign_small_kernel" or "assign_fused_kernel"; static string). */
+const char *b200_assign_kernel_name(const b200_graph *g);
 
 /* S5 - get_state features (reference :751-819).  Inputs: flow real [B][E], dmg/goal uint8 [B][E],
  * tstt f64 [B].  Outputs fp32: node_feat [B][N][4], edge_feat [B][E][6]; capacity_damage is the

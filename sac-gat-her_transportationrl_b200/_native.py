@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
     "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
-    "b200_assign_launches", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_assign_launches", "b200_assign_kernel_name", "b200_state_features", "b200_apply_actions", "b200_reward_done",
     "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
 ]
 
@@ -102,6 +102,7 @@ _vp, _i, _d, _f = C.c_void_p, C.c_int, C.c_double, C.c_float
 
 def _declare(lib) -> None:
     lib.b200_last_error.restype = C.c_char_p
+    lib.b200_assign_kernel_name.restype = C.c_char_p
     lib.b200_version.restype = _i
     lib.b200_graph_create.argtypes = [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp)]
     lib.b200_graph_destroy.argtypes = [_vp]
@@ -114,6 +115,7 @@ def _declare(lib) -> None:
                                        _i, _vp]
     lib.b200_assign.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp]
     lib.b200_assign_launches.argtypes = [_vp]
+    lib.b200_assign_kernel_name.argtypes = [_vp]
     lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]
     lib.b200_apply_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
     lib.b200_reward_done.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp]
@@ -121,7 +123,7 @@ def _declare(lib) -> None:
     lib.b200_gat_edge_softmax_aggregate_bwd.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp,
                                                         _vp, _vp, _vp]
     for name in EXPORTS:
-        if name not in ("b200_last_error",):
+        if name not in ("b200_last_error", "b200_assign_kernel_name"):
             getattr(lib, name).restype = _i
 
 

@@ -197,3 +197,11 @@ extern "C" int b200_graph_origins(const b200_graph *g, int32_t *origins_host)
 }
 
 extern "C" int b200_assign_launches(const b200_graph *g) { return g ? g->last_launches : 0; }
+
+extern "C" const char *b200_assign_kernel_name(const b200_graph *g)
+{
+    if (!g) return "";
+    if (g->static_ok && !g->force_general && !g->force_small) return "assign_static_kernel";
+    if (g->small_ok && !g->force_general) return "assign_small_kernel";
+    return "assign_fused_kernel";
+}

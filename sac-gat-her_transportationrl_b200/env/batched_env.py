@@ -68,6 +68,11 @@ class AssignmentEngine:
         self.N, self.E, self.O = network.num_nodes, network.num_edges, network.num_origins
         self.launches = 0
 
+    @property
+    def kernel_name(self) -> str:
+        """Which fused kernel ``assign`` dispatches to for this network."""
+        return self.lib.b200_assign_kernel_name(self.h).decode()
+
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
