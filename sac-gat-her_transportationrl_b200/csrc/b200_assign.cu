@@ -27,7 +27,7 @@ namespace {
 template <typename REAL>
 struct Cta {
     uint64_t *bar;
-    const int32_t *in_ptr, *in_src, *in_eid;
+    const int32_t *in_ptr, *in_src, *in_eid, *out_ptr, *out_dst;
     int32_t *topo;
     double *w;
     REAL *aux, *flow;
@@ -35,6 +35,10 @@ struct Cta {
     unsigned char *warp_base;
     size_t warp_stride;
     int N, E;
+    bool intq;   // link loads are accumulated as int32 in the aux array (exact, order-independent)
+
+    // link load of link e as REAL, whatever the accumulation type
+    __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
 
     __device__ void carve(unsigned char *smem, const Params &p, int warps)
     {
@@ -44,6 +48,9 @@ struct Cta {
         in_ptr = topo;
         in_src = topo + p.off_in_src;
         in_eid = topo + p.off_in_eid;
+        out_ptr = topo + p.off_out_ptr;
+        out_dst = topo + p.off_out_dst;
+        intq = p.intq != 0;
         w = (double *)(smem + L.off_w);
         aux = (REAL *)(smem + L.off_aux);
         flow = (REAL *)(smem + L.off_flow);
@@ -54,7 +61,7 @@ struct Cta {
         E = p.E;
     }
     __device__ double *dist(int warp) const { return (double *)(warp_base + warp_stride * warp); }
-    __device__ int32_t *pk(int warp) const { return (int32_t *)(warp_base + warp_stride * warp + align16((size_t)N * 8)); }
+    __device__ uint16_t *pk(int warp) const { return (uint16_t *)(warp_base + warp_stride * warp + warp_offsets(N).pk); }
 
     // Stage the static topology into shared memory with one TMA bulk copy (UBLKCP).
     __device__ void stage_topology(const Params &p)
@@ -99,82 +106,176 @@ __device__ void cta_costs_from_flow(Cta<REAL> &c, const Params &p, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// S2: one warp, one origin - label-correcting shortest paths + predecessor selection
+// S2: one warp, one origin - frontier-driven label correcting + predecessor selection
 // ---------------------------------------------------------------------------------------------
+constexpr int kNoPk = 0xFFFF;
+
+struct WarpScratch {
+    double *dist;
+    uint16_t *pk, *q0, *q1;
+    uint32_t *cntw, *mask;
+    int *tail;
+};
 template <typename REAL>
-__device__ int warp_sssp(const Cta<REAL> &c, int origin, double *dist, int32_t *pk)
+__device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp)
+{
+    unsigned char *base = c.warp_base + c.warp_stride * warp;
+    const WarpOffsets W = warp_offsets(c.N);
+    WarpScratch s;
+    s.dist = (double *)base;
+    s.pk = (uint16_t *)(base + W.pk);
+    s.q0 = (uint16_t *)(base + W.q0);
+    s.q1 = (uint16_t *)(base + W.q1);
+    s.cntw = (uint32_t *)(base + W.cnt);
+    s.mask = (uint32_t *)(base + W.mask);
+    s.tail = (int *)(base + W.tail);
+    return s;
+}
+
+// Distances are relaxed to the least fixed point of dist[v] = min_u fl(dist[u] + w(u,v)) (see the
+// file header).  Work is driven by a frontier: a node is re-examined (pull over its in-links) only
+// after one of its in-neighbours improved; the "queued" bit of a node is cleared before its
+// in-neighbours are read, so an improvement that lands after the read re-queues the node for the
+// next round.  Rounds <= longest shortest path in hops.
+template <typename REAL>
+__device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s)
 {
     const int lane = threadIdx.x & 31, N = c.N;
+    double *dist = s.dist;
     for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
+    for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
+    __syncwarp();
+    uint16_t *cur = s.q0, *nxt = s.q1;
+    const int o0 = c.out_ptr[origin];
+    int count = c.out_ptr[origin + 1] - o0;
+    for (int j = lane; j < count; j += 32) {
+        const int x = c.out_dst[o0 + j];
+        cur[j] = (uint16_t)x;
+        atomicOr(&s.mask[x >> 5], 1u << (x & 31));
+    }
     __syncwarp();
     int rounds = 0, capped = 0;
-    for (;;) {
-        bool changed = false;
-        for (int v0 = 0; v0 < N; v0 += 32) {
-            const int v = v0 + lane;
-            double best = 0.0, dv = 0.0;
-            if (v < N) {
-                dv = dist[v];
-                best = dv;
+    while (count > 0) {
+        if (lane == 0) *s.tail = 0;
+        __syncwarp();
+        for (int base = 0; base < count; base += 32) {
+            const bool valid = base + lane < count;
+            const int v = valid ? (int)cur[base + lane] : 0;
+            if (valid) atomicAnd(&s.mask[v >> 5], ~(1u << (v & 31)));
+            __syncwarp();
+            if (valid) {
+                const double dv = dist[v];
+                double best = dv;
                 const int k1 = c.in_ptr[v + 1];
                 for (int k = c.in_ptr[v]; k < k1; ++k) {
                     const double cand = dist[c.in_src[k]] + c.w[k];
                     best = cand < best ? cand : best;
                 }
-            }
-            __syncwarp();  // all reads of this chunk are done before anyone overwrites
-            if (v < N && best < dv) {
-                dist[v] = best;
-                changed = true;
+                if (best < dv) {
+                    dist[v] = best;
+                    const int j1 = c.out_ptr[v + 1];
+                    for (int j = c.out_ptr[v]; j < j1; ++j) {
+                        const int x = c.out_dst[j];
+                        const uint32_t bit = 1u << (x & 31);
+                        if (x != origin && !(atomicOr(&s.mask[x >> 5], bit) & bit)) nxt[atomicAdd(s.tail, 1)] = (uint16_t)x;
+                    }
+                }
             }
             __syncwarp();
         }
-        if (!__any_sync(0xffffffffu, changed)) break;
+        count = *s.tail;
+        uint16_t *t = cur; cur = nxt; nxt = t;
         if (++rounds > N + 1) { capped = 1; break; }
     }
     // predecessor: tight in-link with the smallest dist[u], then the largest u
     for (int v = lane; v < N; v += 32) {
         const double dv = dist[v];
-        int bk = -1, bu = -1;
+        int bk = kNoPk, bu = -1;
         double bdu = B200_INF_F64;
         if (v != origin && dv < B200_INF_F64) {
             const int k1 = c.in_ptr[v + 1];
             for (int k = c.in_ptr[v]; k < k1; ++k) {
                 const int u = c.in_src[k];
                 const double du = dist[u];
-                if (du + c.w[k] == dv && (bk < 0 || du < bdu || (du == bdu && u > bu))) {
+                if (du + c.w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
                     bk = k; bu = u; bdu = du;
                 }
             }
         }
-        pk[v] = bk;
+        s.pk[v] = (uint16_t)bk;
     }
     __syncwarp();
     return capped;
 }
 
 // ---------------------------------------------------------------------------------------------
-// S3: one warp, one origin - walk every destination back to the origin, scatter-add demand
+// S3: one warp, one origin - subtree demand sums, leaves first (Kahn), link loads into c.aux
 // ---------------------------------------------------------------------------------------------
-template <typename REAL>
-__device__ double warp_aon_walk(Cta<REAL> &c, const Params &p, int slot, int origin, const int32_t *pk)
+// Every tree link is handled once: a node whose children are all done adds its subtree sum to
+// its in-link and to its parent.  The frontier of "ready" nodes is a queue; pending-children
+// counters are 16-bit, two per 32-bit word, updated with 32-bit shared-memory atomics.
+// INTQ: sums are int32 (exact, order-independent); otherwise REAL atomics (order-dependent in the
+// last bits, like any parallel sum).  Returns this lane's share of the unassigned demand.
+template <typename REAL, bool INTQ>
+__device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
-    const int lane = threadIdx.x & 31;
+    using QT = typename std::conditional<INTQ, int, REAL>::type;
+    const int lane = threadIdx.x & 31, N = c.N;
+    QT *sacc = (QT *)s.dist;   // dist is dead once pk is chosen
+    QT *auxq = (QT *)c.aux;
     const REAL *q = (const REAL *)p.od_q;
+    for (int v = lane; v < N; v += 32) sacc[v] = 0;
+    for (int i = lane; i < (N + 1) / 2; i += 32) s.cntw[i] = 0u;
+    __syncwarp();
+    const int jd1 = __ldg(p.od_ptr + slot + 1);
+    for (int j = __ldg(p.od_ptr + slot) + lane; j < jd1; j += 32) sacc[__ldg(p.od_dst + j)] = (QT)q[j];
+    __syncwarp();
     double un = 0.0;
-    const int j1 = __ldg(p.od_ptr + slot + 1);
-    for (int j = __ldg(p.od_ptr + slot) + lane; j < j1; j += 32) {
-        const int d = __ldg(p.od_dst + j);
-        const REAL qj = q[j];
-        if (d == origin || pk[d] < 0) { un += (double)qj; continue; }
-        int cur = d, hops = 0;
-        while (cur != origin && hops++ <= c.N) {
-            const int k = pk[cur];
-            atomicAdd(&c.aux[c.in_eid[k]], qj);
-            cur = c.in_src[k];
+    for (int v = lane; v < N; v += 32) {
+        const int k = s.pk[v];
+        if (k != kNoPk) {
+            const int u = c.in_src[k];
+            atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
+        } else {
+            un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
         }
     }
+    __syncwarp();
+    uint16_t *cur = s.q0, *nxt = s.q1;
+    int count = 0;
+    for (int v0 = 0; v0 < N; v0 += 32) {
+        const int v = v0 + lane;
+        bool leaf = false;
+        if (v < N && s.pk[v] != kNoPk) leaf = ((s.cntw[v >> 1] >> ((v & 1) * 16)) & 0xffffu) == 0u;
+        const unsigned m = __ballot_sync(0xffffffffu, leaf);
+        if (leaf) cur[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+        count += __popc(m);
+    }
+    __syncwarp();
+    while (count > 0) {
+        if (lane == 0) *s.tail = 0;
+        __syncwarp();
+        for (int idx = lane; idx < count; idx += 32) {
+            const int v = cur[idx], k = s.pk[v], u = c.in_src[k];
+            const QT sv = sacc[v];
+            if (sv != (QT)0) {
+                atomicAdd(&auxq[c.in_eid[k]], sv);
+                atomicAdd(&sacc[u], sv);
+            }
+            const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
+            if (((old >> ((u & 1) * 16)) & 0xffffu) == 1u && u != origin) nxt[atomicAdd(s.tail, 1)] = (uint16_t)u;
+        }
+        __syncwarp();
+        count = *s.tail;
+        uint16_t *t = cur; cur = nxt; nxt = t;
+    }
     return un;
+}
+
+template <typename REAL>
+__device__ __forceinline__ double warp_aon(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
+{
+    return c.intq ? warp_aon_peel<REAL, true>(c, p, slot, origin, s) : warp_aon_peel<REAL, false>(c, p, slot, origin, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -186,7 +287,7 @@ __device__ double ls_derivative(Cta<REAL> &c, const Params &p, const uint8_t *dm
     double g = 0.0;
     for (int k = threadIdx.x; k < c.E; k += blockDim.x) {
         const int e = c.in_eid[k];
-        const double f = (double)c.flow[e], d = (double)c.aux[e] - f;
+        const double f = (double)c.flow[e], d = (double)c.auxv(e) - f;
         double te;
         if (dmg_b[e]) te = 1e6;
         else te = Bpr<double>::eval(f + lam * d, (double)__ldg(p.cap0_csc + k), (double)__ldg(p.t0_csc + k), p.alpha,
@@ -205,7 +306,7 @@ __device__ void cta_update(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b, 
         for (int k = threadIdx.x; k < c.E; k += blockDim.x) {
             const int e = c.in_eid[k];
             sft += (double)c.flow[e] * c.w[k];
-            sat += (double)c.aux[e] * c.w[k];
+            sat += (double)c.auxv(e) * c.w[k];
         }
         sft = c.block_sum(sft);
         sat = c.block_sum(sat);
@@ -217,7 +318,7 @@ __device__ void cta_update(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b, 
         if (it > 0) {
             double num = 0.0, den = 0.0;
             for (int e = threadIdx.x; e < c.E; e += blockDim.x) {
-                const REAL dir = c.aux[e] - c.flow[e], dp = dprev_b[e];
+                const REAL dir = c.auxv(e) - c.flow[e], dp = dprev_b[e];
                 num += (double)dir * (double)(dir - dp);
                 den += (double)dp * (double)dp;
             }
@@ -230,7 +331,7 @@ __device__ void cta_update(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b, 
         const REAL lam = (REAL)(2.0 / (it + 2.0));
         for (int k = threadIdx.x; k < c.E; k += blockDim.x) {
             const int e = c.in_eid[k];
-            REAL dir = c.aux[e] - c.flow[e];
+            REAL dir = c.auxv(e) - c.flow[e];
             if (it > 0) dir = radd<REAL>(dir, rmul<REAL>(bb, dprev_b[e]));
             REAL f = radd<REAL>(c.flow[e], rmul<REAL>(lam, dir));
             f = f > (REAL)0 ? f : (REAL)0;  // np.maximum(., 0); a NaN ends as 0 after nan_to_num
@@ -257,7 +358,7 @@ __device__ void cta_update(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b, 
         const REAL lam = (REAL)lam64, oml = (REAL)(1.0 - lam64);
         for (int k = threadIdx.x; k < c.E; k += blockDim.x) {
             const int e = c.in_eid[k];
-            REAL f = radd<REAL>(rmul<REAL>(oml, c.flow[e]), rmul<REAL>(lam, c.aux[e]));
+            REAL f = radd<REAL>(rmul<REAL>(oml, c.flow[e]), rmul<REAL>(lam, c.auxv(e)));
             if (f != f) { f = 0; saw_nan = 1; }
             c.flow[e] = f;
             c.w[k] = (double)link_cost<REAL>(p, k, f, dmg_b[e] != 0);
@@ -320,15 +421,14 @@ __global__ void __launch_bounds__(kMaxWarps * 32) sssp_kernel(Params p)
         int capped = 0;
         for (int s = warp; s < p.O; s += W) {
             const int o = __ldg(p.origins + s);
-            double *dist = c.dist(warp);
-            int32_t *pk = c.pk(warp);
-            capped |= warp_sssp<REAL>(c, o, dist, pk);
+            const WarpScratch ws = warp_scratch(c, warp);
+            capped |= warp_sssp<REAL>(c, o, ws);
             const size_t base = ((size_t)b * p.O + s) * p.N;
             for (int v = lane; v < p.N; v += 32) {
-                const int k = pk[v];
-                p.dist_out[base + v] = dist[v];
-                p.pred_out[base + v] = k < 0 ? B200_NO_PRED : c.in_src[k];
-                p.pedge_out[base + v] = k < 0 ? -1 : c.in_eid[k];
+                const int k = ws.pk[v];
+                p.dist_out[base + v] = ws.dist[v];
+                p.pred_out[base + v] = k == kNoPk ? B200_NO_PRED : c.in_src[k];
+                p.pedge_out[base + v] = k == kNoPk ? -1 : c.in_eid[k];
             }
             __syncwarp();
         }
@@ -355,18 +455,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32) aon_kernel(Params p)
         double un = 0.0;
         for (int s = warp; s < p.O; s += W) {
             const int o = __ldg(p.origins + s);
-            int32_t *pk = c.pk(warp);
+            const WarpScratch ws = warp_scratch(c, warp);
             const int32_t *pe = p.pedge_in + ((size_t)b * p.O + s) * p.N;
-            for (int v = lane; v < p.N; v += 32) { const int e = pe[v]; pk[v] = e < 0 ? -1 : slot_of[e]; }
+            for (int v = lane; v < p.N; v += 32) { const int e = pe[v]; ws.pk[v] = (uint16_t)(e < 0 ? kNoPk : slot_of[e]); }
             __syncwarp();
-            un += warp_aon_walk<REAL>(c, p, s, o, pk);
+            un += warp_aon<REAL>(c, p, s, o, ws);
             __syncwarp();
         }
         un = warp_sum_f64(un);
         if (lane == 0 && un != 0.0) atomicAdd(&c.red[kMaxWarps * 2], un);
         __syncthreads();
         REAL *aux_b = (REAL *)p.aux + (size_t)b * p.E;
-        for (int e = threadIdx.x; e < c.E; e += blockDim.x) aux_b[e] = c.aux[e];
+        for (int e = threadIdx.x; e < c.E; e += blockDim.x) aux_b[e] = c.auxv(e);
         if (threadIdx.x == 0) p.unassigned[b] = c.red[kMaxWarps * 2];
     }
 }
@@ -378,6 +478,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) update_kernel(Params p)
     Cta<REAL> c;
     const int W = blockDim.x >> 5;
     c.carve(smem, p, W);
+    c.intq = false;   // aux comes from HBM as REAL here
     c.stage_topology(p);
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
         const size_t off = (size_t)b * p.E;
@@ -441,8 +542,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
             int capped = 0;
             for (int s = warp; s < p.O; s += W) {
                 const int o = __ldg(p.origins + s);
-                capped |= warp_sssp<REAL>(c, o, c.dist(warp), c.pk(warp));
-                un += warp_aon_walk<REAL>(c, p, s, o, c.pk(warp));
+                const WarpScratch ws = warp_scratch(c, warp);
+                capped |= warp_sssp<REAL>(c, o, ws);
+                un += warp_aon<REAL>(c, p, s, o, ws);
                 __syncwarp();
             }
             un = warp_sum_f64(un);
@@ -475,6 +577,8 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     memset(&p, 0, sizeof(p));
     p.N = g->N; p.E = g->E; p.O = g->O; p.topo_ints = g->topo_ints;
     p.off_in_src = g->off_in_src; p.off_in_eid = g->off_in_eid;
+    p.off_out_ptr = g->off_out_ptr; p.off_out_dst = g->off_out_dst;
+    p.intq = g->gen_intq;
     p.topo = g->topo; p.row = g->row; p.origins = g->origins; p.od_ptr = g->od_ptr; p.od_dst = g->od_dst;
     p.t0_csc = g->t0_csc; p.cap0_csc = g->cap0_csc; p.t0 = g->t0; p.cap0 = g->cap0;
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
@@ -510,6 +614,7 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
 {
     const int rb = prec == B200_F32 ? 4 : 8;
     int best = -1;
+    if (g->N > 65534 || g->E > 65534) return -1;   // tree slots and queues are 16-bit
     double best_score = -1.0;
     for (int w = kMinWarps; w <= kMaxWarps; ++w) {
         SmemLayout L = make_layout(g->N, g->E, g->topo_ints, w, rb);

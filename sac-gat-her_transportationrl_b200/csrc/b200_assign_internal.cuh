@@ -19,6 +19,28 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Per-warp scratch of the general kernel (one origin at a time):
+//   dist f64 [N] (aliased by the subtree sums once the tree is chosen) | pk u16 [N] tree in-link slot
+//   | q0, q1 u16 [N] frontier queues | cnt u16 [N] pending children (updated with 32-bit atomics on
+//   the containing word) | mask u32 [ceil(N/32)] "already queued" bits | tail counter
+struct WarpOffsets {
+    size_t pk, q0, q1, cnt, mask, tail, total;
+};
+__host__ __device__ inline WarpOffsets warp_offsets(int N)
+{
+    WarpOffsets W;
+    size_t o = align16((size_t)N * 8);
+    W.pk = o;   o += align16((size_t)N * 2);
+    W.q0 = o;   o += align16((size_t)N * 2);
+    W.q1 = o;   o += align16((size_t)N * 2);
+    W.cnt = o;  o += align16((size_t)((N + 1) / 2) * 4);
+    W.mask = o; o += align16((size_t)((N + 31) / 32) * 4);
+    W.tail = o; o += 16;
+    W.total = o;
+    return W;
+}
+__host__ __device__ inline size_t warp_scratch_bytes(int N) { return warp_offsets(N).total; }
+
 struct SmemLayout {
     size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
 };
@@ -34,7 +56,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_ints, i
     L.off_flow = o; o += align16((size_t)E * real_bytes);
     L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
     L.off_warp = o;
-    L.warp_stride = align16((size_t)N * 8) + align16((size_t)N * 4);
+    L.warp_stride = warp_scratch_bytes(N);
     L.total = o + L.warp_stride * warps;
     return L;
 }
@@ -48,7 +70,8 @@ struct SmallOffsets {
 struct Params {
     SmallOffsets so;
     // static network
-    int N, E, O, topo_ints, off_in_src, off_in_eid;
+    int N, E, O, topo_ints, off_in_src, off_in_eid, off_out_ptr, off_out_dst;
+    int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads
     const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
     const float *t0_csc, *cap0_csc, *t0, *cap0;
     const void *od_q;  // REAL

@@ -41,6 +41,7 @@ void b200_set_error(const char *fmt, ...);
 //   int32 in_ptr[N+1 (+pad)]   CSC: in-links of node v are slots in_ptr[v] .. in_ptr[v+1]-1
 //   int32 in_src[E (+pad)]     tail node of the link in CSC slot k
 //   int32 in_eid[E (+pad)]     original link id (TNTP row order) of CSC slot k
+//   int32 out_ptr[N+1 (+pad)] | out_dst[E (+pad)]   out-links by tail node (frontier expansion)
 // In-links of a node are stored in ascending tail-node order.
 struct b200_graph {
     int device;
@@ -50,6 +51,9 @@ struct b200_graph {
     int32_t *topo;
     int topo_ints;  // padded to a multiple of 4 ints (16 B)
     int off_in_ptr, off_in_src, off_in_eid;
+    // appended for the general fused kernel: out-link CSR (out_ptr[N+1] | out_dst[E]), same blob so
+    // one TMA copy stages everything; gen_intq = all demands are integers (total < 2^31)
+    int off_out_ptr, off_out_dst, gen_intq;
     // per-link attributes, TNTP order
     int32_t *row, *col;
     float *t0, *cap0;

@@ -3,6 +3,7 @@
 #include "b200_common.cuh"
 
 #include <algorithm>
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -132,11 +133,20 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     g->off_in_ptr = 0;
     g->off_in_src = pad4(N + 1);
     g->off_in_eid = g->off_in_src + pad4(E);
-    g->topo_ints = g->off_in_eid + pad4(E);
+    g->off_out_ptr = g->off_in_eid + pad4(E);
+    g->off_out_dst = g->off_out_ptr + pad4(N + 1);
+    g->topo_ints = g->off_out_dst + pad4(E);
     std::vector<int32_t> blob(g->topo_ints, 0);
     std::copy(in_ptr.begin(), in_ptr.end(), blob.begin() + g->off_in_ptr);
     std::copy(in_src.begin(), in_src.end(), blob.begin() + g->off_in_src);
     std::copy(in_eid.begin(), in_eid.end(), blob.begin() + g->off_in_eid);
+    std::copy(out_ptr.begin(), out_ptr.end(), blob.begin() + g->off_out_ptr);
+    std::copy(out_dst.begin(), out_dst.end(), blob.begin() + g->off_out_dst);
+    {
+        bool intq = total < 2147483648.0;
+        for (int k = 0; k < num_od && intq; ++k) intq = od_q[k] >= 0.0 && od_q[k] == floor(od_q[k]);
+        g->gen_intq = intq ? 1 : 0;
+    }
     int rc;
     if ((rc = upload(&g->topo, blob))) return rc;
     std::vector<int32_t> vrow(row, row + E), vcol(col, col + E);
