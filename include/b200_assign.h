@@ -11,7 +11,8 @@
  *  - every function returns 0 on success, a negative B200_E* code or a positive cudaError_t;
  *    b200_last_error() returns a static string for the calling thread's last failure;
  *  - all array arguments of the compute calls are DEVICE pointers owned by the caller (torch
- *    tensors in our host code); the library allocates nothing per call; calls are asynchronous
+ *    tensors in our host code); the library allocates nothing per call (one exception: the general
+ *    fused kernel keeps a trees workspace inside the handle, grown on first use); calls are asynchronous
  *    on the caller's stream (pass the cudaStream_t as a void*; NULL = legacy default stream);
  *  - batch layout: [B][E] / [B][O][N] row-major, one scenario per row ("scenario-major");
  *  - prec: B200_F32 keeps the reference's dtypes (fp32 flow/cost/TSTT sum, fp64 distances),

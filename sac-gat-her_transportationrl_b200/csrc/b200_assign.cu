@@ -137,53 +137,131 @@ __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp
 // after one of its in-neighbours improved; the "queued" bit of a node is cleared before its
 // in-neighbours are read, so an improvement that lands after the read re-queues the node for the
 // next round.  Rounds <= longest shortest path in hops.
+// Warm start (tree != nullptr: this origin's tree of the previous iteration, in-link slot per node):
+// the old tree is re-evaluated top-down under the new costs - every label is then the length of a
+// real path, i.e. a valid upper bound - and ALL nodes are queued once, so the first round is a
+// full verification pass and later rounds only follow actual changes.  The fixed point, and with
+// it the result, is the same as from a cold start.
+// Queue tails live in a warp-uniform register: new entries are placed by ballot + popcount, the
+// only shared-memory atomics are the "already queued" bits.  Link loops are unrolled by kLinkUnroll
+// so the dependent shared-memory loads of one step are issued together.
+constexpr int kLinkUnroll = 4;
+
 template <typename REAL>
-__device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s)
+__device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, const uint16_t *tree = nullptr)
 {
     const int lane = threadIdx.x & 31, N = c.N;
+    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     double *dist = s.dist;
     for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
-    for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
-    __syncwarp();
     uint16_t *cur = s.q0, *nxt = s.q1;
-    const int o0 = c.out_ptr[origin];
-    int count = c.out_ptr[origin + 1] - o0;
-    for (int j = lane; j < count; j += 32) {
-        const int x = c.out_dst[o0 + j];
-        cur[j] = (uint16_t)x;
-        atomicOr(&s.mask[x >> 5], 1u << (x & 31));
+    int count;
+    if (tree) {
+        for (int v = lane; v < N; v += 32) s.pk[v] = tree[v];
+        if (lane == 0) cur[0] = (uint16_t)origin;
+        __syncwarp();
+        count = 1;
+        while (count > 0) {   // breadth-first over the old tree's children
+            int ntail = 0;
+            for (int base = 0; base < count; base += 32) {
+                const bool valid = base + lane < count;
+                const int u = valid ? (int)cur[base + lane] : 0;
+                const double du = valid ? dist[u] : 0.0;
+                const int j0 = valid ? c.out_ptr[u] : 0, j1 = valid ? c.out_ptr[u + 1] : 0;
+                for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
+                    int xs[kLinkUnroll], ks[kLinkUnroll];
+#pragma unroll
+                    for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? c.out_dst[j0 + jb + i] : -1;
+#pragma unroll
+                    for (int i = 0; i < kLinkUnroll; ++i) ks[i] = xs[i] >= 0 ? (int)s.pk[xs[i]] : kNoPk;
+#pragma unroll
+                    for (int i = 0; i < kLinkUnroll; ++i) {
+                        const bool child = ks[i] != kNoPk && c.in_src[ks[i]] == u;
+                        if (child) dist[xs[i]] = du + c.w[ks[i]];
+                        const unsigned m = __ballot_sync(FULL, child);
+                        if (child) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
+                        ntail += __popc(m);
+                    }
+                }
+            }
+            __syncwarp();
+            count = ntail;
+            uint16_t *t = cur; cur = nxt; nxt = t;
+        }
+        // queue every node but the origin
+        for (int v = lane; v < N; v += 32)
+            if (v != origin) cur[v - (v > origin ? 1 : 0)] = (uint16_t)v;
+        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0xffffffffu;
+        count = N - 1;
+        __syncwarp();
+        if (lane == 0) atomicAnd(&s.mask[origin >> 5], ~(1u << (origin & 31)));
+    } else {
+        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
+        __syncwarp();
+        const int o0 = c.out_ptr[origin];
+        count = c.out_ptr[origin + 1] - o0;
+        for (int j = lane; j < count; j += 32) {
+            const int x = c.out_dst[o0 + j];
+            cur[j] = (uint16_t)x;
+            atomicOr(&s.mask[x >> 5], 1u << (x & 31));
+        }
     }
     __syncwarp();
     int rounds = 0, capped = 0;
     while (count > 0) {
-        if (lane == 0) *s.tail = 0;
-        __syncwarp();
+        int ntail = 0;
         for (int base = 0; base < count; base += 32) {
             const bool valid = base + lane < count;
             const int v = valid ? (int)cur[base + lane] : 0;
             if (valid) atomicAnd(&s.mask[v >> 5], ~(1u << (v & 31)));
             __syncwarp();
+            bool improved = false;
             if (valid) {
                 const double dv = dist[v];
                 double best = dv;
-                const int k1 = c.in_ptr[v + 1];
-                for (int k = c.in_ptr[v]; k < k1; ++k) {
-                    const double cand = dist[c.in_src[k]] + c.w[k];
-                    best = cand < best ? cand : best;
-                }
-                if (best < dv) {
-                    dist[v] = best;
-                    const int j1 = c.out_ptr[v + 1];
-                    for (int j = c.out_ptr[v]; j < j1; ++j) {
-                        const int x = c.out_dst[j];
-                        const uint32_t bit = 1u << (x & 31);
-                        if (x != origin && !(atomicOr(&s.mask[x >> 5], bit) & bit)) nxt[atomicAdd(s.tail, 1)] = (uint16_t)x;
+                const int k0 = c.in_ptr[v], k1 = c.in_ptr[v + 1];
+                for (int kb = k0; kb < k1; kb += kLinkUnroll) {
+                    int us[kLinkUnroll];
+                    double ws[kLinkUnroll];
+#pragma unroll
+                    for (int i = 0; i < kLinkUnroll; ++i) {
+                        const bool ok = kb + i < k1;
+                        us[i] = ok ? c.in_src[kb + i] : v;
+                        ws[i] = ok ? c.w[kb + i] : B200_INF_F64;
                     }
+#pragma unroll
+                    for (int i = 0; i < kLinkUnroll; ++i) {
+                        const double cand = dist[us[i]] + ws[i];
+                        best = cand < best ? cand : best;
+                    }
+                }
+                improved = best < dv;
+                if (improved) dist[v] = best;
+            }
+            const int j0 = improved ? c.out_ptr[v] : 0, j1 = improved ? c.out_ptr[v + 1] : 0;
+            for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
+                int xs[kLinkUnroll];
+                bool fresh[kLinkUnroll];
+#pragma unroll
+                for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? c.out_dst[j0 + jb + i] : -1;
+#pragma unroll
+                for (int i = 0; i < kLinkUnroll; ++i) {
+                    fresh[i] = false;
+                    if (xs[i] >= 0 && xs[i] != origin) {
+                        const uint32_t bit = 1u << (xs[i] & 31);
+                        fresh[i] = !(atomicOr(&s.mask[xs[i] >> 5], bit) & bit);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < kLinkUnroll; ++i) {
+                    const unsigned m = __ballot_sync(FULL, fresh[i]);
+                    if (fresh[i]) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
+                    ntail += __popc(m);
                 }
             }
             __syncwarp();
         }
-        count = *s.tail;
+        count = ntail;
         uint16_t *t = cur; cur = nxt; nxt = t;
         if (++rounds > N + 1) { capped = 1; break; }
     }
@@ -252,21 +330,29 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
         count += __popc(m);
     }
     __syncwarp();
+    const unsigned lt = (1u << lane) - 1u;
     while (count > 0) {
-        if (lane == 0) *s.tail = 0;
-        __syncwarp();
-        for (int idx = lane; idx < count; idx += 32) {
-            const int v = cur[idx], k = s.pk[v], u = c.in_src[k];
-            const QT sv = sacc[v];
-            if (sv != (QT)0) {
-                atomicAdd(&auxq[c.in_eid[k]], sv);
-                atomicAdd(&sacc[u], sv);
+        int ntail = 0;
+        for (int base = 0; base < count; base += 32) {
+            bool ready = false;
+            int u = 0;
+            if (base + lane < count) {
+                const int v = cur[base + lane], k = s.pk[v];
+                u = c.in_src[k];
+                const QT sv = sacc[v];
+                if (sv != (QT)0) {
+                    atomicAdd(&auxq[c.in_eid[k]], sv);
+                    atomicAdd(&sacc[u], sv);
+                }
+                const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
+                ready = ((old >> ((u & 1) * 16)) & 0xffffu) == 1u && u != origin;   // that was the last child
             }
-            const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
-            if (((old >> ((u & 1) * 16)) & 0xffffu) == 1u && u != origin) nxt[atomicAdd(s.tail, 1)] = (uint16_t)u;
+            const unsigned m = __ballot_sync(0xffffffffu, ready);
+            if (ready) nxt[ntail + __popc(m & lt)] = (uint16_t)u;
+            ntail += __popc(m);
         }
         __syncwarp();
-        count = *s.tail;
+        count = ntail;
         uint16_t *t = cur; cur = nxt; nxt = t;
     }
     return un;
@@ -543,7 +629,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
             for (int s = warp; s < p.O; s += W) {
                 const int o = __ldg(p.origins + s);
                 const WarpScratch ws = warp_scratch(c, warp);
-                capped |= warp_sssp<REAL>(c, o, ws);
+                uint16_t *tree = p.tree_ws + ((size_t)blockIdx.x * p.O + s) * p.N;
+                capped |= warp_sssp<REAL>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
+                for (int v = lane; v < p.N; v += 32) tree[v] = ws.pk[v];   // next iteration's warm start
                 un += warp_aon<REAL>(c, p, s, o, ws);
                 __syncwarp();
             }
@@ -578,7 +666,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.N = g->N; p.E = g->E; p.O = g->O; p.topo_ints = g->topo_ints;
     p.off_in_src = g->off_in_src; p.off_in_eid = g->off_in_eid;
     p.off_out_ptr = g->off_out_ptr; p.off_out_dst = g->off_out_dst;
-    p.intq = g->gen_intq;
+    p.intq = g->gen_intq; p.warm = g->warm_start;
     p.topo = g->topo; p.row = g->row; p.origins = g->origins; p.od_ptr = g->od_ptr; p.od_dst = g->od_dst;
     p.t0_csc = g->t0_csc; p.cap0_csc = g->cap0_csc; p.t0 = g->t0; p.cap0 = g->cap0;
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
@@ -591,8 +679,9 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
 }
 
 template <typename K>
-int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p, cudaStream_t st)
+int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_in, cudaStream_t st, bool need_trees = false)
 {
+    Params p = p_in;
     const int warps = prec == B200_F32 ? g->warps_f32 : g->warps_f64;
     const size_t smem = prec == B200_F32 ? g->smem_f32 : g->smem_f64;
     B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -602,6 +691,18 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p, 
     // Small networks: one CTA per scenario, the hardware block scheduler balances the tail and
     // re-staging a sub-8-KB topology is free.  Large networks: persistent CTAs, topology staged once.
     const int grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, per_sm * g->num_sms);
+    if (need_trees) {
+        // previous-iteration trees of the resident CTAs (the only allocation the library ever makes
+        // after graph upload; it grows monotonically and is reused by later calls)
+        const size_t need = (size_t)grid * g->O * g->N * sizeof(uint16_t);
+        b200_graph *gm = const_cast<b200_graph *>(g);
+        if (need > gm->tree_ws_bytes) {
+            if (gm->tree_ws) { B200_CUDA(cudaStreamSynchronize(st)); B200_CUDA(cudaFree(gm->tree_ws)); gm->tree_ws = nullptr; gm->tree_ws_bytes = 0; }
+            B200_CUDA(cudaMalloc((void **)&gm->tree_ws, need));
+            gm->tree_ws_bytes = need;
+        }
+        p.tree_ws = gm->tree_ws;
+    }
     kernel<<<grid, warps * 32, smem, st>>>(p);
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -713,8 +814,8 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
         // Sioux-Falls class: one warp per scenario, lane = origin
         rc = b200_launch_small(g, p, prec, (cudaStream_t)stream);
     } else {
-        rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream)
-                              : launch_cta_kernel(assign_fused_kernel<double>, g, prec, p, (cudaStream_t)stream);
+        rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream, true)
+                              : launch_cta_kernel(assign_fused_kernel<double>, g, prec, p, (cudaStream_t)stream, true);
     }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;
     return rc;

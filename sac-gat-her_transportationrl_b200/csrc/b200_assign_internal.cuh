@@ -71,6 +71,7 @@ struct Params {
     SmallOffsets so;
     // static network
     int N, E, O, topo_ints, off_in_src, off_in_eid, off_out_ptr, off_out_dst;
+    int warm;  // general kernel: warm-start shortest paths from the previous iteration's trees
     int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads
     const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
     const float *t0_csc, *cap0_csc, *t0, *cap0;
@@ -93,6 +94,7 @@ struct Params {
     int32_t *status;
     double *dist_out;                      // [B][O][N]
     int32_t *pred_out, *pedge_out;
+    uint16_t *tree_ws;                     // general fused kernel: [gridDim.x][O][N] previous trees
     const int32_t *pedge_in;
     double alpha, beta, penalty;
 };

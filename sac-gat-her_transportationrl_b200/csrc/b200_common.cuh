@@ -54,6 +54,10 @@ struct b200_graph {
     // appended for the general fused kernel: out-link CSR (out_ptr[N+1] | out_dst[E]), same blob so
     // one TMA copy stages everything; gen_intq = all demands are integers (total < 2^31)
     int off_out_ptr, off_out_dst, gen_intq;
+    // general fused kernel: previous-iteration trees, u16 [resident CTAs][O][N], grown on demand
+    uint16_t *tree_ws;
+    size_t tree_ws_bytes;
+    int warm_start;   // 0 disables the warm start (env B200_NO_WARM, A/B measurements)
     // per-link attributes, TNTP order
     int32_t *row, *col;
     float *t0, *cap0;

@@ -123,6 +123,13 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     // network qualifies for the small-network kernel
     g->force_general = getenv("B200_FORCE_GENERAL") != nullptr;
     g->force_small = getenv("B200_FORCE_SMALL") != nullptr;
+    // Warm-starting the shortest paths from the previous iteration's trees pays when frontiers are
+    // wide (measured: Chicago-Sketch-size lattice, 3.2 links/node, +15 %); on maze-like networks the
+    // top-down pass over a deep tree costs more than it saves (Anaheim-size, 2.2 links/node, -24 %).
+    // B200_NO_WARM / B200_WARM force either (A/B measurements).
+    g->warm_start = (double)E / N >= 2.6;
+    if (getenv("B200_NO_WARM")) g->warm_start = 0;
+    if (getenv("B200_WARM")) g->warm_start = 1;
     g->N = N; g->E = E; g->O = O; g->num_od = num_od; g->max_in_deg = max_in; g->total_demand = total;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -183,7 +190,7 @@ extern "C" int b200_graph_destroy(b200_graph *g)
     void *ptrs[] = {g->topo, g->row, g->col, g->t0, g->cap0, g->t0_csc, g->cap0_csc, g->origins, g->origin_slot,
                     g->od_ptr, g->od_dst, g->od_q64, g->od_q32, g->out_ptr, g->out_dst, g->out_eid,
                     g->small_blob32, g->small_blob64, g->small_blob_i32, g->small_eid, g->small_wpos,
-                    g->st_t0, g->st_cap0, g->st_eid, g->st_wpos, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
+                    g->tree_ws, g->st_t0, g->st_cap0, g->st_eid, g->st_wpos, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(g->origins_host);
