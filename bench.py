@@ -59,47 +59,59 @@ def workload_config(n_gpus: int) -> dict:
 # clocks sampler (nvidia-smi during the timed region)
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons of one GPU, sampled every few ms by a thread through NVML while
+    the timed regions run (the timed region is tens of ms long - too short for `nvidia-smi -lms`,
+    which is only the fallback when pynvml cannot be loaded)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc, self.thread = index, [], None, None
+    def __init__(self, torch_index: int, period_s: float = 0.002):
+        self.index, self.period = torch_index, period_s
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.handle = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception as exc:  # noqa: BLE001
+            self.err = f"pynvml unavailable: {exc}"
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._loop, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+            except Exception as exc:  # noqa: BLE001
+                self.err = str(exc)
+                return
+            time.sleep(self.period)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except Exception:
-                continue
-            for n, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [self.err or "no samples"], "samples": 0}
+        reasons = sorted(name for bit, name in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm), "how": "NVML, 2 ms period, during both timed regions"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -297,7 +309,7 @@ def run_ours(args) -> None:
             "config": workload_config(world),
             "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": UNIT,
                     "h2d_bytes_per_step": int(B * E), "d2h_bytes_per_step": int(B * 8)},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * world,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
@@ -321,7 +333,7 @@ def run_ours(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
