@@ -12,6 +12,8 @@ from .env.network import Network
 from .env.batched_env import AssignmentEngine, BatchedEnvState, BatchedRepairEnv
 from .env.repair_env import EnvState, RepairEnv
 from .models.gat import GATConvB200, GATEncoderB200, gat_edge_softmax_aggregate
+from . import baselines
+from . import rl
 
 import os as _os
 
@@ -31,5 +33,5 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
 __all__ = [
     "AssignmentEngine", "BatchedEnvState", "GATConvB200", "GATEncoderB200", "gat_edge_softmax_aggregate", "BatchedRepairEnv", "EdgeData", "EnvState", "GraphData", "Network",
     "RepairEnv", "build_native", "load_graph_data", "load_sioux_falls", "parse_net_tntp", "parse_trips_tntp",
-    "synthetic",
+    "synthetic", "baselines", "rl",
 ]

@@ -277,6 +277,30 @@ class BatchedRepairEnv:
         self.initial_tstt.copy_(self.tstt)
         return self.get_state()
 
+    def reset_where(self, mask: torch.Tensor, damaged_ratio: Optional[float] = None) -> None:
+        """Per-scenario reset (episode boundaries in a lock-step batch): scenarios with ``mask[b]``
+        get a fresh damage draw (their own generator; the cached draw under ``fixed_damage``),
+        zero flows, goal := damage, a cold-start assignment and a new ``initial_tstt``; the
+        others are untouched.  The reference resets one env at a time (:167-205)."""
+        mask = mask.to(device=self.device, dtype=torch.bool)
+        idx = torch.nonzero(mask, as_tuple=False).squeeze(1)
+        if idx.numel() == 0:
+            return
+        ratio = self.damaged_ratio if damaged_ratio is None else damaged_ratio
+        rows = idx.cpu().tolist()
+        if self.fixed_damage:
+            new = torch.from_numpy(self.sample_damage_masks(ratio)[rows])
+        else:
+            host = np.zeros((len(rows), self.E), dtype=np.uint8)
+            for i, b in enumerate(rows):
+                host[i, self.network.sample_damage(self.rngs[b], ratio)] = 1
+            new = torch.from_numpy(host)
+        self.is_damaged[idx] = new.to(self.device)
+        self.goal_mask[idx] = self.is_damaged[idx]
+        self.flow[idx] = 0
+        self.compute_flow_assignment(active=mask.to(torch.uint8))
+        self.initial_tstt[idx] = self.tstt[idx]
+
     def compute_flow_assignment(self, active: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.engine.assign(self.is_damaged, self.flow, self.assignment_iters, self.assignment_method, self._out,
                            self._dprev, active)

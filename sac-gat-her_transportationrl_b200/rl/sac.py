@@ -1,0 +1,215 @@
+"""Discrete soft actor-critic over link-repair actions, dense-batched on a fixed topology.
+
+Reference: src/rl/sac.py - ``Actor`` (:23-46), ``Critic`` (:49-78), ``DiscreteSAC`` (:81-287).
+The reference batches graphs the PyG way (concatenated nodes/links + a ``batch`` vector,
+``torch_geometric.utils.softmax`` / ``torch_scatter.scatter_sum`` per graph).  Every scenario has
+the same topology here, so a batch is ``node_x [B,N,F]``, ``edge_attr [B,E,F]``,
+``action_mask [B,E]``: the per-graph softmax is a row softmax, ``scatter_sum`` is ``sum(dim=1)``
+and the per-item ``nonzero`` action indexing of src/train.py:841-845 disappears (the action is
+the link id).  Module and parameter names are the reference's, so ``state_dict`` layouts match
+(``actor.encoder.layers.0.lin.weight`` ...) and ``save`` / ``load`` use the reference's file
+layout (:265-287).  The GAT message passing runs in the CUDA kernel of ``models/gat.py``; the
+dense projections are torch GEMMs.
+
+Multi-GPU: ``update`` averages gradients over ranks (NCCL all-reduce, ``dist.py``) before every
+optimiser step when ``torch.distributed`` is initialised - a data-parallel learner.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..dist import allreduce_mean_gradients
+from ..env.network import Network
+from ..models.gat import GATEncoderB200
+
+
+@dataclass
+class SACOutput:
+    action: torch.Tensor  # [B] link ids
+    log_prob: torch.Tensor  # [B]
+    probs: torch.Tensor  # [B, E]
+
+
+class _EdgeHead(nn.Module):
+    """Shared body of Actor and Critic: norms -> encoder -> per-link MLP on
+    [emb(src) | emb(dst) | edge_attr | global mean||max context]."""
+
+    def __init__(self, network: Network, node_in: int, edge_in: int, hidden: int, embed: int, num_layers: int = 3,
+                 encoder: Optional[GATEncoderB200] = None):
+        super().__init__()
+        self.node_norm = nn.LayerNorm(node_in)
+        self.edge_norm = nn.LayerNorm(edge_in)
+        self.encoder = encoder if encoder is not None else GATEncoderB200(network, node_in, hidden, embed,
+                                                                          edge_dim=edge_in, num_layers=num_layers)
+        self.edge_mlp = nn.Sequential(nn.Linear(embed * 4 + edge_in, hidden), nn.ReLU(), nn.Linear(hidden, 1))
+        self.register_buffer("_src", torch.from_numpy(network.edge_index[0].copy()), persistent=False)
+        self.register_buffer("_dst", torch.from_numpy(network.edge_index[1].copy()), persistent=False)
+
+    def edge_scores(self, node_x, edge_attr, return_attention: bool = False):
+        node_x = self.node_norm(node_x)
+        edge_attr = self.edge_norm(edge_attr)
+        node_emb, ctx, attn = self.encoder(node_x, edge_attr, return_attention=return_attention)
+        B, E = edge_attr.shape[0], edge_attr.shape[1]
+        edge_emb = torch.cat([node_emb[:, self._src], node_emb[:, self._dst], edge_attr,
+                              ctx.unsqueeze(1).expand(B, E, ctx.shape[-1])], dim=2)
+        return self.edge_mlp(edge_emb).squeeze(-1), attn
+
+
+class Actor(_EdgeHead):
+    def forward(self, node_x, edge_attr, action_mask, return_attention: bool = False):
+        logits, attn = self.edge_scores(node_x, edge_attr, return_attention)
+        logits = logits.masked_fill(action_mask <= 0, -1e9)
+        probs = torch.softmax(logits, dim=1)  # PyG softmax per graph = row softmax on a fixed topology
+        return logits, probs, attn
+
+
+class Critic(_EdgeHead):
+    def forward(self, node_x, edge_attr):
+        q, _ = self.edge_scores(node_x, edge_attr)
+        return q
+
+
+class DiscreteSAC:
+    def __init__(self, network: Network, node_in: int, edge_in: int, hidden: int, embed: int, num_layers: int = 3,
+                 lr: float = 3e-4, actor_lr: Optional[float] = None, critic_lr: Optional[float] = None,
+                 alpha_lr: Optional[float] = None, grad_clip: Optional[float] = None, gamma: float = 0.99,
+                 target_tau: float = 0.005, target_entropy: Optional[float] = None, target_entropy_ratio: float = 0.1,
+                 alpha_init: float = 0.1, share_critic_encoder: bool = True, device="cuda"):
+        dev = torch.device(device)
+        self.device = dev
+        mk = dict(network=network, node_in=node_in, edge_in=edge_in, hidden=hidden, embed=embed, num_layers=num_layers)
+        self.actor = Actor(**mk).to(dev)
+        self.share_critic_encoder = share_critic_encoder
+        if share_critic_encoder:
+            enc = lambda: GATEncoderB200(network, node_in, hidden, embed, edge_dim=edge_in, num_layers=num_layers)  # noqa: E731
+            self.critic_encoder, self.target_encoder = enc().to(dev), enc().to(dev)
+            self.critic1 = Critic(**mk, encoder=self.critic_encoder).to(dev)
+            self.critic2 = Critic(**mk, encoder=self.critic_encoder).to(dev)
+            self.target1 = Critic(**mk, encoder=self.target_encoder).to(dev)
+            self.target2 = Critic(**mk, encoder=self.target_encoder).to(dev)
+            self.target_encoder.load_state_dict(self.critic_encoder.state_dict())
+        else:
+            self.critic1, self.critic2 = Critic(**mk).to(dev), Critic(**mk).to(dev)
+            self.target1, self.target2 = Critic(**mk).to(dev), Critic(**mk).to(dev)
+            self.target1.load_state_dict(self.critic1.state_dict())
+            self.target2.load_state_dict(self.critic2.state_dict())
+        for m in (self.target1, self.target2):
+            for p in m.parameters():
+                p.requires_grad_(False)
+        actor_lr = lr if actor_lr is None else actor_lr
+        critic_lr = lr if critic_lr is None else critic_lr
+        alpha_lr = lr if alpha_lr is None else alpha_lr
+        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=actor_lr)
+        if share_critic_encoder:
+            # exactly the reference's list (:119-123): the critics' input LayerNorms are not optimised
+            self.critic_params = (list(self.critic_encoder.parameters()) + list(self.critic1.edge_mlp.parameters())
+                                  + list(self.critic2.edge_mlp.parameters()))
+        else:
+            self.critic_params = list(self.critic1.parameters()) + list(self.critic2.parameters())
+        self.critic_opt = torch.optim.Adam(self.critic_params, lr=critic_lr)
+        self.log_alpha = torch.tensor(float(np.log(max(alpha_init, 1e-8))), requires_grad=True, device=dev)
+        self.alpha_opt = torch.optim.Adam([self.log_alpha], lr=alpha_lr)
+        self.gamma, self.target_tau = gamma, target_tau
+        self.target_entropy, self.target_entropy_ratio, self.grad_clip = target_entropy, target_entropy_ratio, grad_clip
+
+    @property
+    def alpha(self):
+        return self.log_alpha.exp()
+
+    @torch.no_grad()
+    def select_action(self, node_x, edge_attr, action_mask, deterministic: bool = False,
+                      generator: Optional[torch.Generator] = None) -> SACOutput:
+        """Batched ``select_action`` (:147-157): one action per scenario."""
+        _, probs, _ = self.actor(node_x, edge_attr, action_mask)
+        action = torch.argmax(probs, dim=1) if deterministic else torch.multinomial(probs, 1, generator=generator).squeeze(1)
+        log_prob = torch.log(probs.gather(1, action.unsqueeze(1)).squeeze(1) + 1e-8)
+        return SACOutput(action=action, log_prob=log_prob, probs=probs)
+
+    def update(self, batch: Dict[str, torch.Tensor], weights: Optional[torch.Tensor] = None,
+               alpha_max: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """One learner step on a dense batch (keys of ``DeviceReplay.store``); losses as in :159-263."""
+        f32 = lambda k: batch[k].to(self.device, torch.float32)  # noqa: E731
+        node_x, edge_attr, mask = f32("node_x"), f32("edge_attr"), f32("action_mask")
+        nnode_x, nedge_attr, nmask = f32("next_node_x"), f32("next_edge_attr"), f32("next_action_mask")
+        action = batch["action"].to(self.device, torch.int64).unsqueeze(1)
+        reward, done = f32("reward"), f32("done")
+        w = torch.ones_like(reward) if weights is None else weights.to(self.device, torch.float32).expand_as(reward)
+        with torch.no_grad():
+            _, next_probs, _ = self.actor(nnode_x, nedge_attr, nmask)
+            q_next = torch.min(self.target1(nnode_x, nedge_attr), self.target2(nnode_x, nedge_attr))
+            v_next = (next_probs * (q_next - self.alpha * torch.log(next_probs + 1e-8))).sum(dim=1)
+            target = reward + (1.0 - done) * self.gamma * v_next
+        q1_all, q2_all = self.critic1(node_x, edge_attr), self.critic2(node_x, edge_attr)
+        q1, q2 = q1_all.gather(1, action).squeeze(1), q2_all.gather(1, action).squeeze(1)
+        td_error = (target - q1).detach().abs()
+        critic_loss = (w * (F.mse_loss(q1, target, reduction="none") + F.mse_loss(q2, target, reduction="none"))).mean()
+        self.critic_opt.zero_grad(set_to_none=True)
+        critic_loss.backward()
+        allreduce_mean_gradients(self.critic_params)
+        if self.grad_clip:
+            torch.nn.utils.clip_grad_norm_(self.critic_params, max_norm=self.grad_clip)
+        self.critic_opt.step()
+
+        _, probs, _ = self.actor(node_x, edge_attr, mask)
+        q_all = torch.min(q1_all, q2_all).detach()
+        log_p = torch.log(probs + 1e-8)
+        actor_loss = (probs * (self.alpha.detach() * log_p - q_all)).sum(dim=1).mean()
+        self.actor_opt.zero_grad(set_to_none=True)
+        actor_loss.backward()
+        actor_params = list(self.actor.parameters())
+        allreduce_mean_gradients(actor_params)
+        if self.grad_clip:
+            torch.nn.utils.clip_grad_norm_(actor_params, max_norm=self.grad_clip)
+        self.actor_opt.step()
+
+        if self.target_entropy is None:
+            target_entropy = (self.target_entropy_ratio * torch.log((mask > 0).float().sum(dim=1) + 1e-8)).mean()
+        else:
+            target_entropy = self.target_entropy
+        probs_d, log_pd = probs.detach(), log_p.detach()
+        alpha_loss = -(self.log_alpha * (probs_d * (log_pd + target_entropy)).sum(dim=1)).mean()
+        self.alpha_opt.zero_grad(set_to_none=True)
+        alpha_loss.backward()
+        allreduce_mean_gradients([self.log_alpha])
+        if self.grad_clip:
+            torch.nn.utils.clip_grad_norm_([self.log_alpha], max_norm=self.grad_clip)
+        self.alpha_opt.step()
+        with torch.no_grad():
+            if alpha_max is not None:
+                self.log_alpha.clamp_(max=float(np.log(alpha_max)))
+            self.log_alpha.clamp_(min=float(np.log(0.01)))
+            if self.share_critic_encoder:
+                self._soft_update(self.critic_encoder, self.target_encoder)
+                self._soft_update(self.critic1.edge_mlp, self.target1.edge_mlp)
+                self._soft_update(self.critic2.edge_mlp, self.target2.edge_mlp)
+            else:
+                self._soft_update(self.critic1, self.target1)
+                self._soft_update(self.critic2, self.target2)
+        return {"critic_loss": critic_loss.detach(), "actor_loss": actor_loss.detach(), "alpha": self.alpha.detach(),
+                "alpha_loss": alpha_loss.detach(), "policy_entropy": -(probs_d * log_pd).sum(dim=1).mean(),
+                "q_taken": torch.min(q1, q2).detach().mean(), "q_mean": q_all.mean(), "td_errors": td_error}
+
+    @torch.no_grad()
+    def _soft_update(self, src: nn.Module, tgt: nn.Module) -> None:
+        for p, tp in zip(src.parameters(), tgt.parameters()):
+            tp.lerp_(p, self.target_tau)
+
+    # ---- checkpoints in the reference's layout (:265-287) ---------------------------------------
+    def save(self, path: str) -> None:
+        torch.save({"actor": self.actor.state_dict(), "critic1": self.critic1.state_dict(),
+                    "critic2": self.critic2.state_dict(), "target1": self.target1.state_dict(),
+                    "target2": self.target2.state_dict(), "log_alpha": self.log_alpha.detach().cpu()}, path)
+
+    def load(self, path: str, map_location="cpu", strict: bool = True) -> None:
+        state = torch.load(path, map_location=map_location, weights_only=True)
+        self.actor.load_state_dict(state["actor"], strict=strict)
+        for name in ("critic1", "critic2", "target1", "target2"):
+            getattr(self, name).load_state_dict(state[name], strict=strict)
+        with torch.no_grad():
+            self.log_alpha.copy_(state["log_alpha"].to(self.device))

@@ -1,0 +1,167 @@
+"""Batched SAC + GAT + PER training loop (BASELINE.json config 5).
+
+Reference: src/train.py - rollout workers (:138-214) push pickled transitions through an
+``mp.Queue``; the learner (:735-900) adds them to the replay one by one, samples, relabels (HER),
+assembles PyG batches and updates; actor weights go back through another queue (:863-874).
+
+Here one process per GPU owns ``num_envs`` scenarios in a ``BatchedRepairEnv``, the actor, the
+critics and a device replay.  Per env step, on every rank:
+  1. one batched actor forward picks an action per scenario (no weight broadcast: the learner and
+     the rollout share the module);
+  2. ``env.step`` = one fused assignment launch + reward/done/feature kernels;
+  3. the step's transitions are all-gathered over NCCL into every rank's replay (identical
+     replay contents on all ranks, sampled with rank-specific generators);
+  4. every ``update_every`` steps, ``updates_per_step`` learner updates with gradients averaged
+     over ranks (NCCL all-reduce);
+  5. scenarios that are done (or hit ``max_steps``) are reset in place.
+The config keys are the reference's YAML keys (configs/sioux_falls.yaml); ``num_envs`` is new.
+"""
+from __future__ import annotations
+
+import time
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from ..dist import all_gather_transitions
+from ..env.batched_env import REWARD_MODES, BatchedRepairEnv, _ptr
+from .. import _native
+from .replay import DeviceReplay
+from .sac import DiscreteSAC
+
+
+def default_config() -> Dict:
+    """Defaults of the reference's ``configs/sioux_falls.yaml`` that matter for the loop (the
+    shipped file sets ``assignment_method: cfw``)."""
+    return dict(num_envs=1024, damaged_ratio=0.3, assignment_iters=60, assignment_method="cfw", buffer_size=1_000_000,
+                batch_start=2000, update_every=4, updates_per_step=1, batch_size=256, per_alpha=0.6, per_beta=0.4,
+                per_eps=1e-6, reward_scale=0.5, reward_mode="rel_improve", reward_alpha=1.0, reward_beta=0.0,
+                reward_gamma=0.0, reward_clip=2.0, fixed_damage=True, fixed_damage_seed=42, capacity_damage=1e-3,
+                unassigned_penalty=1e4, max_steps=100, her_ratio=0.0, gat_layers=3, hidden_dim=256, embed_dim=256,
+                lr=1e-4, actor_lr=3e-5, critic_lr=1e-4, alpha_lr=1e-4, gamma=0.99, target_tau=0.001, grad_clip=1.0,
+                share_critic_encoder=False, seed=42, alpha_max=2.5, alpha_init=0.1, target_entropy_ratio=0.2,
+                precision="fp32")
+
+
+class BatchedTrainer:
+    def __init__(self, graph_data, cfg: Optional[Dict] = None, device="cuda"):
+        self.cfg = default_config()
+        self.cfg.update(cfg or {})
+        c = self.cfg
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.device = torch.device(device)
+        B = int(c["num_envs"])
+        seeds = [c["seed"] + self.rank * B + b for b in range(B)]
+        self.env = BatchedRepairEnv(
+            graph_data, B, damaged_ratio=c["damaged_ratio"], assignment_iters=c["assignment_iters"],
+            assignment_method=c["assignment_method"], device=self.device, precision=c["precision"],
+            reward_mode=c["reward_mode"], reward_alpha=c["reward_alpha"], reward_beta=c["reward_beta"],
+            reward_gamma=c["reward_gamma"], reward_clip=c["reward_clip"], capacity_damage=c["capacity_damage"],
+            unassigned_penalty=c["unassigned_penalty"], fixed_damage=c["fixed_damage"],
+            fixed_damage_seed=c["fixed_damage_seed"], seeds=seeds)
+        net = self.env.network
+        torch.manual_seed(c["seed"])  # identical initial weights on every rank
+        self.agent = DiscreteSAC(net, 4, 6, c["hidden_dim"], c["embed_dim"], num_layers=c["gat_layers"], lr=c["lr"],
+                                 actor_lr=c["actor_lr"], critic_lr=c["critic_lr"], alpha_lr=c["alpha_lr"],
+                                 grad_clip=c["grad_clip"], gamma=c["gamma"], target_tau=c["target_tau"],
+                                 target_entropy_ratio=c["target_entropy_ratio"], alpha_init=c["alpha_init"],
+                                 share_critic_encoder=c["share_critic_encoder"], device=self.device)
+        self.replay = DeviceReplay(int(c["buffer_size"]), net.num_nodes, net.num_edges, alpha=c["per_alpha"],
+                                   beta=c["per_beta"], eps=c["per_eps"], device=self.device)
+        self.gen = torch.Generator(device=self.device).manual_seed(c["seed"] * 7919 + self.rank)
+        self.state = self.env.reset()
+        self.ep_steps = torch.zeros(B, dtype=torch.int64, device=self.device)
+        self.ep_reward = torch.zeros(B, dtype=torch.float64, device=self.device)
+        self.global_steps = 0
+        self.stats = dict(env_steps=0, assignments=B, updates=0, episodes=0, nccl_ms=0.0, wall_s=0.0,
+                          episode_reward_sum=0.0, last_losses={})
+
+    # reward of a relabelled goal, through the same kernel the env uses (reference :244-291)
+    def _reward_fn(self, prev, nxt, init, next_mask, goal):
+        n = prev.shape[0]
+        c, eng = self.cfg, self.env.engine
+        reward = torch.empty(n, dtype=torch.float64, device=self.device)
+        done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        dmg = next_mask.to(torch.uint8).contiguous()
+        goal = goal.to(torch.uint8).contiguous()
+        _native.check(eng.lib.b200_reward_done(
+            eng.h, n, REWARD_MODES.get(c["reward_mode"], 0), _ptr(prev.contiguous()), _ptr(nxt.contiguous()),
+            _ptr(init.contiguous()), _ptr(dmg), _ptr(goal), None, float(c["reward_alpha"]), float(c["reward_beta"]),
+            float(c["reward_gamma"]), float(c["reward_clip"] or 0.0), _ptr(reward), _ptr(done), eng._stream()),
+            "b200_reward_done")
+        return reward, done
+
+    def _timed_collective(self, fn):
+        if self.world == 1:
+            return fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn()
+        e.record()
+        self._pending_events.append((s, e))
+        return out
+
+    def step(self) -> None:
+        """One lock-step env step of every scenario + the learner updates that are due."""
+        c, env, st = self.cfg, self.env, self.state
+        self._pending_events = []
+        out = self.agent.select_action(st.node_features, st.edge_features, st.action_mask, generator=self.gen)
+        actions = out.action.to(torch.int32)
+        prev_tstt = env.tstt.clone()
+        nst, reward, done, info = env.step(actions)
+        local = {
+            "node_x": st.node_features, "edge_attr": st.edge_features, "action_mask": st.action_mask.to(torch.uint8),
+            "next_node_x": nst.node_features, "next_edge_attr": nst.edge_features,
+            "next_action_mask": nst.action_mask.to(torch.uint8), "action": actions.to(torch.int64),
+            "reward": (reward * c["reward_scale"]).float(), "done": done.float(), "prev_tstt": prev_tstt,
+            "next_tstt": info["tstt"], "initial_tstt": env.initial_tstt.clone(),
+        }
+        gathered = self._timed_collective(lambda: all_gather_transitions(local))
+        self.replay.add_batch(gathered)
+        self.global_steps += 1
+        self.stats["env_steps"] += env.num_envs * self.world
+        self.stats["assignments"] += int(info["valid"].sum()) * self.world  # invalid actions skip the assignment
+        self.ep_steps += 1
+        self.ep_reward += reward * c["reward_scale"]
+        if self.replay.size > c["batch_start"] and self.global_steps % c["update_every"] == 0:
+            for _ in range(c["updates_per_step"]):
+                bs = min(c["batch_size"], self.replay.size)
+                batch, idx, w = self.replay.sample(bs, generator=self.gen)
+                batch = DeviceReplay.relabel_hindsight(batch, c["her_ratio"], self._reward_fn, c["reward_scale"], self.gen)
+                losses = self.agent.update(batch, weights=w, alpha_max=c["alpha_max"])
+                self.replay.update_priorities(idx, losses["td_errors"])
+                self.stats["updates"] += 1
+                self.stats["last_losses"] = losses
+        finished = done | (self.ep_steps >= c["max_steps"]) if c["max_steps"] > 0 else done
+        n_fin = int(finished.sum())
+        if n_fin:
+            self.stats["episodes"] += n_fin * self.world
+            self.stats["episode_reward_sum"] += float(self.ep_reward[finished].sum())
+            env.reset_where(finished)
+            self.stats["assignments"] += n_fin * self.world
+            self.ep_steps[finished] = 0
+            self.ep_reward[finished] = 0
+            nst = env.get_state()
+        self.state = nst
+        if self._pending_events:
+            torch.cuda.synchronize(self.device)
+            self.stats["nccl_ms"] += sum(s.elapsed_time(e) for s, e in self._pending_events)
+
+    def run(self, env_steps: int) -> Dict:
+        """``env_steps`` lock-step steps; returns throughput figures (whole job, all ranks)."""
+        torch.cuda.synchronize(self.device)
+        t0 = time.perf_counter()
+        base = dict(self.stats)
+        for _ in range(env_steps):
+            self.step()
+        torch.cuda.synchronize(self.device)
+        wall = time.perf_counter() - t0
+        self.stats["wall_s"] += wall
+        d = {k: self.stats[k] - base[k] for k in ("env_steps", "assignments", "updates", "episodes", "nccl_ms")}
+        losses = {k: float(v) for k, v in self.stats["last_losses"].items() if k != "td_errors"}
+        return {"env_steps_per_s": d["env_steps"] / wall, "assignments_per_s": d["assignments"] / wall,
+                "updates_per_s": d["updates"] / wall, "episodes": d["episodes"], "wall_s": wall,
+                "nccl_time_share": d["nccl_ms"] / 1e3 / wall, "world_size": self.world, "losses": losses,
+                "replay_size": self.replay.size, "mean_tstt": float(self.env.tstt.mean())}

@@ -1,0 +1,117 @@
+"""GPU tests of the learner side: actor/critic on the CUDA GAT kernel, SAC update, checkpoint
+layout, the batched trainer loop (BASELINE.json config 5 at toy size)."""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rl():
+    return importlib.import_module("sac-gat-her_transportationrl_b200.rl")
+
+
+def test_actor_critic_shapes_masking_and_reference_state_dict_layout(b200env, native_lib, sf_graph):
+    rl = _rl()
+    net = b200env.Network(sf_graph)
+    dev = torch.device("cuda", 0)
+    actor = rl.Actor(net, 4, 6, 32, 16, num_layers=3).to(dev)
+    critic = rl.Critic(net, 4, 6, 32, 16, num_layers=3).to(dev)
+    B = 5
+    x, ea = torch.rand(B, 24, 4, device=dev), torch.rand(B, 76, 6, device=dev)
+    mask = (torch.rand(B, 76, device=dev) > 0.6).float()
+    mask[0] = 0  # no valid action: uniform, like PyG's softmax over an all -1e9 row
+    logits, probs, attn = actor(x, ea, mask, return_attention=True)
+    assert probs.shape == (B, 76) and attn.shape == (B, 76 + 24, 1)
+    torch.testing.assert_close(probs.sum(dim=1), torch.ones(B, device=dev))
+    assert torch.all(probs[1:][mask[1:] <= 0] < 1e-20)
+    torch.testing.assert_close(probs[0], torch.full((76,), 1 / 76, device=dev))
+    assert critic(x, ea).shape == (B, 76)
+    keys = set(actor.state_dict())
+    # the reference's (PyG GATConv) parameter names, src/rl/sac.py:23-33 + gat_encoder.py:20-31
+    for k in ("node_norm.weight", "edge_norm.bias", "encoder.layers.0.lin.weight", "encoder.layers.0.lin_edge.weight",
+              "encoder.layers.0.att_src", "encoder.layers.0.att_dst", "encoder.layers.0.att_edge",
+              "encoder.layers.2.bias", "encoder.input_proj.weight", "encoder.norms.2.weight", "edge_mlp.0.weight",
+              "edge_mlp.2.bias"):
+        assert k in keys, k
+    assert actor.state_dict()["encoder.layers.0.lin.weight"].shape == (4 * 32, 4)
+    assert actor.state_dict()["edge_mlp.0.weight"].shape == (32, 16 * 4 + 6)
+
+
+def _dense_reference_losses(agent, batch, weights):
+    """The reference's loss formulas (src/rl/sac.py:190-224) written per graph with python loops."""
+    with torch.no_grad():
+        f = lambda k: batch[k].float()  # noqa: E731
+        _, nprobs, _ = agent.actor(f("next_node_x"), f("next_edge_attr"), f("next_action_mask"))
+        qn = torch.min(agent.target1(f("next_node_x"), f("next_edge_attr")), agent.target2(f("next_node_x"), f("next_edge_attr")))
+        q1 = agent.critic1(f("node_x"), f("edge_attr"))
+        q2 = agent.critic2(f("node_x"), f("edge_attr"))
+        _, probs, _ = agent.actor(f("node_x"), f("edge_attr"), f("action_mask"))
+        crit, act = 0.0, 0.0
+        B = q1.shape[0]
+        for b in range(B):
+            v = sum(float(nprobs[b, e]) * (float(qn[b, e]) - float(agent.alpha) * np.log(float(nprobs[b, e]) + 1e-8))
+                    for e in range(q1.shape[1]))
+            tgt = float(batch["reward"][b]) + (1.0 - float(batch["done"][b])) * agent.gamma * v
+            a = int(batch["action"][b])
+            crit += float(weights[b]) * ((float(q1[b, a]) - tgt) ** 2 + (float(q2[b, a]) - tgt) ** 2)
+            qa = torch.min(q1[b], q2[b])
+            act += sum(float(probs[b, e]) * (float(agent.alpha) * np.log(float(probs[b, e]) + 1e-8) - float(qa[e]))
+                       for e in range(q1.shape[1]))
+        return crit / B, act / B
+
+
+def test_sac_update_matches_per_graph_formulas_and_checkpoint_roundtrip(b200env, native_lib, sf_graph, tmp_path):
+    rl = _rl()
+    net = b200env.Network(sf_graph)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    agent = rl.DiscreteSAC(net, 4, 6, 32, 16, num_layers=3, lr=1e-3, grad_clip=1.0, share_critic_encoder=False, device=dev)
+    B = 6
+    g = torch.Generator(device=dev).manual_seed(3)
+    batch = {
+        "node_x": torch.rand(B, 24, 4, device=dev, generator=g), "edge_attr": torch.rand(B, 76, 6, device=dev, generator=g),
+        "action_mask": (torch.rand(B, 76, device=dev, generator=g) > 0.5).to(torch.uint8),
+        "next_node_x": torch.rand(B, 24, 4, device=dev, generator=g),
+        "next_edge_attr": torch.rand(B, 76, 6, device=dev, generator=g),
+        "next_action_mask": (torch.rand(B, 76, device=dev, generator=g) > 0.5).to(torch.uint8),
+        "action": torch.randint(0, 76, (B,), device=dev, generator=g), "reward": torch.rand(B, device=dev, generator=g),
+        "done": torch.tensor([0, 0, 1, 0, 1, 0], device=dev).float(),
+    }
+    w = torch.rand(B, device=dev, generator=g) + 0.5
+    crit_ref, act_ref = _dense_reference_losses(agent, batch, w)
+    before = [p.detach().clone() for p in agent.actor.parameters()]
+    out = agent.update(batch, weights=w, alpha_max=2.5)
+    assert float(out["critic_loss"]) == pytest.approx(crit_ref, rel=2e-4, abs=1e-6)
+    assert float(out["actor_loss"]) == pytest.approx(act_ref, rel=2e-4, abs=1e-6)
+    assert out["td_errors"].shape == (B,) and torch.all(torch.isfinite(out["td_errors"]))
+    assert any(not torch.equal(a, b) for a, b in zip(before, agent.actor.parameters()))
+    for s_, t_ in ((agent.critic1, agent.target1),):  # polyak: target moved a little towards the critic
+        d = sum(float((p - tp).abs().sum()) for p, tp in zip(s_.parameters(), t_.parameters()))
+        assert d > 0
+    path = tmp_path / "model.pt"
+    agent.save(str(path))
+    state = torch.load(str(path), weights_only=True)
+    assert set(state) == {"actor", "critic1", "critic2", "target1", "target2", "log_alpha"}  # reference :265-276
+    other = rl.DiscreteSAC(net, 4, 6, 32, 16, num_layers=3, share_critic_encoder=False, device=dev)
+    other.load(str(path), map_location=dev)
+    for a, b in zip(agent.actor.parameters(), other.actor.parameters()):
+        assert torch.equal(a, b)
+    assert float(other.log_alpha) == pytest.approx(float(agent.log_alpha))
+
+
+def test_batched_trainer_runs_episodes_updates_and_resets(b200env, native_lib, sf_graph):
+    rl = _rl()
+    cfg = dict(num_envs=32, assignment_iters=5, assignment_method="msa", buffer_size=4096, batch_start=64, update_every=2,
+               batch_size=32, hidden_dim=32, embed_dim=16, max_steps=6, her_ratio=0.5, fixed_damage=False,
+               damaged_ratio=0.1, reward_mode="log_delta", reward_clip=0.0, reward_beta=10.0, reward_gamma=0.1)
+    tr = rl.BatchedTrainer(sf_graph, cfg, device="cuda:0")
+    res = tr.run(12)
+    assert res["env_steps_per_s"] > 0 and res["updates_per_s"] > 0 and res["episodes"] >= 32
+    assert tr.replay.size == 12 * 32
+    assert all(np.isfinite(v) for v in res["losses"].values())
+    assert int(tr.ep_steps.max()) <= 6
+    # a reset scenario is a fresh episode: damage restored to 7 links, flows re-assigned
+    assert torch.all(tr.env.is_damaged.sum(dim=1) <= 7) and torch.all(tr.env.tstt > 0)
