@@ -716,14 +716,19 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
     const int rb = prec == B200_F32 ? 4 : 8;
     int best = -1;
     if (g->N > 65534 || g->E > 65534) return -1;   // tree slots and queues are 16-bit
+    // The kernel is latency-bound (dependent shared-memory loads, few active lanes per round), so what
+    // counts is how many origins an SM works on at once: resident warps = warps per CTA x CTAs per
+    // SM (shared memory: 227 KB per SM, 1 KB reserved per CTA), weighted by how evenly the origins
+    // divide among the warps.  Ties go to fewer warps per CTA (more CTAs = more scenarios in flight).
     double best_score = -1.0;
     for (int w = kMinWarps; w <= kMaxWarps; ++w) {
         SmemLayout L = make_layout(g->N, g->E, g->topo_ints, w, rb);
         if (L.total > kSmemLimit) break;
         const int O = std::max(g->O, 1);
         const double eff = (double)O / (double)(((O + w - 1) / w) * w);
-        const double score = eff - 0.004 * (w > 8 ? w - 8 : 8 - w);  // prefer ~8 warps on ties
-        if (score > best_score) { best_score = score; best = w; }
+        const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
+        const double score = eff * w * std::max(ctas, 1);
+        if (score > best_score + 1e-9) { best_score = score; best = w; }
     }
     if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo_ints, best, rb).total;
     return best;
