@@ -19,6 +19,9 @@
 // largest u" reproduces scipy's trees bit for bit.
 #include "b200_assign_internal.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 using namespace b200i;
 
 namespace {
@@ -598,19 +601,68 @@ __global__ void __launch_bounds__(kMaxWarps * 32) update_kernel(Params p)
     }
 }
 
+// Thread-block cluster mode (few scenarios, many origins: e.g. 32 Chicago-Sketch-size scenarios
+// per GPU): the C CTAs of a cluster share ONE scenario and split its origins.  Each CTA loads its
+// origins' trees into its own aux[]; after a cluster barrier every CTA pulls the other CTAs'
+// partial link loads through distributed shared memory, in rank order, so all C copies of the
+// total are bit-identical; each CTA then runs S4 redundantly on its own copy of flow / w (cheap:
+// O(E)), which avoids any further exchange.  Two cluster barriers per iteration.
+template <typename REAL, bool INTQ>
+__device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double *un_s, int *flag_s)
+{
+    using QT = typename std::conditional<INTQ, int, REAL>::type;
+    constexpr int CH = 16;
+    const unsigned C = cluster.num_blocks();
+    QT *mine = (QT *)c.aux;
+    double un = 0.0;
+    int flags = 0;
+    if (threadIdx.x == 0) {
+        for (unsigned r = 0; r < C; ++r) {
+            un += *cluster.map_shared_rank(un_s, r);
+            const int *f = cluster.map_shared_rank(flag_s, r);
+            flags |= (f[0] ? 1 : 0) | (f[1] ? 2 : 0);
+        }
+    }
+    for (int base = 0; base < c.E; base += CH * (int)blockDim.x) {
+        QT acc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int e = base + j * (int)blockDim.x + (int)threadIdx.x;
+            acc[j] = 0;
+            if (e < c.E)
+                for (unsigned r = 0; r < C; ++r) acc[j] += ((const QT *)cluster.map_shared_rank(c.aux, r))[e];
+        }
+        cluster.sync();   // everybody has read this range (and, first pass, the scalars)
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            const int e = base + j * (int)blockDim.x + (int)threadIdx.x;
+            if (e < c.E) mine[e] = acc[j];
+        }
+    }
+    if (threadIdx.x == 0) {
+        *un_s = un;
+        flag_s[0] = flags & 1;
+        flag_s[1] = (flags >> 1) & 1;
+    }
+    __syncthreads();
+}
+
 // The fused path: K iterations of S1..S4 with every per-scenario array in shared memory.
 template <typename REAL>
 __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     Cta<REAL> c;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     c.carve(smem, p, W);
     c.stage_topology(p);
     double *un_s = &c.red[kMaxWarps * 2];
     int *flag_s = (int *)&c.red[kMaxWarps * 2 + 1];
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        if (p.active && !p.active[b]) continue;  // CTA-uniform
+    const int cluster_id = blockIdx.x / C, num_clusters = gridDim.x / C;
+    for (int b = cluster_id; b < p.B; b += num_clusters) {
+        if (p.active && !p.active[b]) continue;  // cluster-uniform
         const size_t off = (size_t)b * p.E;
         REAL *flow_b = (REAL *)p.flow + off;
         const uint8_t *dmg_b = p.dmg + off;
@@ -623,13 +675,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
         for (int it = 0; it < p.K; ++it) {
             for (int e = threadIdx.x; e < c.E; e += blockDim.x) c.aux[e] = 0;
             if (threadIdx.x == 0) *un_s = 0.0;
-            __syncthreads();
+            __syncthreads();   // (neighbours finished pulling last iteration's loads before its last cluster barrier)
             double un = 0.0;
             int capped = 0;
-            for (int s = warp; s < p.O; s += W) {
+            for (int s = rank * W + warp; s < p.O; s += C * W) {
                 const int o = __ldg(p.origins + s);
                 const WarpScratch ws = warp_scratch(c, warp);
-                uint16_t *tree = p.tree_ws + ((size_t)blockIdx.x * p.O + s) * p.N;
+                uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + s) * p.N;
                 capped |= warp_sssp<REAL>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
                 for (int v = lane; v < p.N; v += 32) tree[v] = ws.pk[v];   // next iteration's warm start
                 un += warp_aon<REAL>(c, p, s, o, ws);
@@ -639,6 +691,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
             if (lane == 0 && un != 0.0) atomicAdd(un_s, un);
             if (capped && lane == 0) flag_s[1] = 1;
             __syncthreads();
+            if (C > 1) {
+                cluster.sync();   // every CTA's partial loads are complete
+                if (c.intq) cluster_combine<REAL, true>(c, cluster, un_s, flag_s);
+                else cluster_combine<REAL, false>(c, cluster, un_s, flag_s);
+            }
             int nan_seen = 0;
             cta_update<REAL>(c, p, dmg_b, it, dprev_b, it == p.K - 1, p.gap + b, &nan_seen);
             if (nan_seen) flag_s[0] = 1;
@@ -646,13 +703,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
         }
         const double un_final = *un_s;
         cta_tstt<REAL>(c, p, c.aux, un_final, p.tstt + b);
-        for (int e = threadIdx.x; e < c.E; e += blockDim.x) flow_b[e] = c.flow[e];
-        if (threadIdx.x == 0) {
-            p.unassigned[b] = un_final;
-            p.status[b] = (flag_s[0] ? B200_ST_NAN_FLOW : 0) | (un_final > 0.0 ? B200_ST_UNASSIGNED : 0) |
-                          (flag_s[1] ? B200_ST_SSSP_CAP : 0);
+        if (rank == 0) {
+            for (int e = threadIdx.x; e < c.E; e += blockDim.x) flow_b[e] = c.flow[e];
+            if (threadIdx.x == 0) {
+                p.unassigned[b] = un_final;
+                p.status[b] = (flag_s[0] ? B200_ST_NAN_FLOW : 0) | (un_final > 0.0 ? B200_ST_UNASSIGNED : 0) |
+                              (flag_s[1] ? B200_ST_SSSP_CAP : 0);
+            }
         }
     }
+    if (C > 1) cluster.sync();   // no CTA exits while a neighbour may still read its shared memory
 }
 
 
@@ -679,7 +739,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
 }
 
 template <typename K>
-int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_in, cudaStream_t st, bool need_trees = false)
+int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_in, cudaStream_t st, bool fused = false)
 {
     Params p = p_in;
     const int warps = prec == B200_F32 ? g->warps_f32 : g->warps_f64;
@@ -690,11 +750,39 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
     if (per_sm < 1) { b200_set_error("kernel does not fit on an SM (smem %zu)", smem); return B200_EUNSUPPORTED; }
     // Small networks: one CTA per scenario, the hardware block scheduler balances the tail and
     // re-staging a sub-8-KB topology is free.  Large networks: persistent CTAs, topology staged once.
-    const int grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, per_sm * g->num_sms);
-    if (need_trees) {
-        // previous-iteration trees of the resident CTAs (the only allocation the library ever makes
-        // after graph upload; it grows monotonically and is reused by later calls)
-        const size_t need = (size_t)grid * g->O * g->N * sizeof(uint16_t);
+    const int capacity = per_sm * g->num_sms;
+    int grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, capacity);
+    int cluster = 1;
+    if (fused) {
+        // Fewer scenarios than resident CTAs: split every scenario's origins over a thread-block
+        // cluster (power of two <= 8, no more CTAs than batches of `warps` origins).  cfw keeps one
+        // CTA per scenario (its direction scratch lives in the caller's [B][E] array).
+        if (g->cluster_limit != 1 && p.method != B200_CFW) {
+            const int want = std::min({8, g->cluster_limit > 0 ? g->cluster_limit : 8, capacity / std::max(p.B, 1),
+                                       (g->O + warps - 1) / warps});
+            while (cluster * 2 <= want) cluster *= 2;
+        }
+        if (cluster > 1) {
+            cudaLaunchConfig_t probe = {};
+            probe.gridDim = dim3(cluster);
+            probe.blockDim = dim3(warps * 32);
+            probe.dynamicSmemBytes = smem;
+            cudaLaunchAttribute pa[1];
+            pa[0].id = cudaLaunchAttributeClusterDimension;
+            pa[0].val.clusterDim.x = cluster; pa[0].val.clusterDim.y = 1; pa[0].val.clusterDim.z = 1;
+            probe.attrs = pa; probe.numAttrs = 1;
+            int max_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &probe) != cudaSuccess || max_clusters < 1) {
+                cudaGetLastError();
+                cluster = 1;
+            } else {
+                grid = cluster * std::min(p.B, max_clusters);
+            }
+        }
+        if (cluster == 1) grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, capacity);
+        // previous-iteration trees of the resident scenarios (the only allocation the library ever
+        // makes after graph upload; it grows monotonically and is reused by later calls)
+        const size_t need = (size_t)(grid / cluster) * g->O * g->N * sizeof(uint16_t);
         b200_graph *gm = const_cast<b200_graph *>(g);
         if (need > gm->tree_ws_bytes) {
             if (gm->tree_ws) { B200_CUDA(cudaStreamSynchronize(st)); B200_CUDA(cudaFree(gm->tree_ws)); gm->tree_ws = nullptr; gm->tree_ws_bytes = 0; }
@@ -702,8 +790,19 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
             gm->tree_ws_bytes = need;
         }
         p.tree_ws = gm->tree_ws;
+        gm->last_cluster = cluster;
     }
-    kernel<<<grid, warps * 32, smem, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster > 1 ? 1 : 0;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -130,6 +130,7 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     g->warm_start = (double)E / N >= 2.6;
     if (getenv("B200_NO_WARM")) g->warm_start = 0;
     if (getenv("B200_WARM")) g->warm_start = 1;
+    g->cluster_limit = getenv("B200_CLUSTER") ? atoi(getenv("B200_CLUSTER")) : 0;
     g->N = N; g->E = E; g->O = O; g->num_od = num_od; g->max_in_deg = max_in; g->total_demand = total;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;

@@ -258,6 +258,34 @@ def test_fused_chicago_sketch_size_vs_reference(b200env, native_lib, golden):
     assert np.array_equal(pred.cpu().numpy()[:, :8, :], G["pred"].astype(np.int32))
 
 
+def test_cluster_mode_matches_single_cta_per_scenario(b200env, native_lib, monkeypatch):
+    """Few scenarios on a large network: the general kernel splits a scenario's origins over a
+    thread-block cluster and combines the partial link loads through distributed shared memory.
+    Integer demands -> int32 sums -> results must be bit-identical to one CTA per scenario."""
+    g = b200env.synthetic.anaheim_size(0)
+    rng = np.random.default_rng(5)
+    dmg = np.zeros((3, 914), np.uint8)
+    for b in range(3):
+        dmg[b, rng.choice(914, 274, replace=False)] = 1
+    monkeypatch.setenv("B200_CLUSTER", "1")
+    single = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_CLUSTER")
+    outs = {}
+    for limit in ("2", "4", "0"):  # 0 = automatic (8 here: 3 scenarios on an empty GPU)
+        monkeypatch.setenv("B200_CLUSTER", limit)
+        outs[limit] = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_CLUSTER")
+    for method in ("fw", "msa"):
+        ref = _assign(single, dmg, 6, method)
+        for limit, eng in outs.items():
+            got = _assign(eng, dmg, 6, method)
+            assert np.array_equal(got["flow"], ref["flow"]), (method, limit)
+            assert np.array_equal(got["tstt"], ref["tstt"]) and np.array_equal(got["status"], ref["status"])
+            np.testing.assert_allclose(got["gap"], ref["gap"], rtol=1e-12)
+    # cfw keeps one CTA per scenario and still agrees with itself
+    assert np.array_equal(_assign(outs["0"], dmg, 4, "cfw")["flow"], _assign(single, dmg, 4, "cfw")["flow"])
+
+
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at full batch size
 # ---------------------------------------------------------------------------------------------

@@ -20,8 +20,11 @@ CASES = {
 
 def main():
     dev = torch.device("cuda", 0)
-    for name in (sys.argv[1:] or ["sf", "an", "cs"]):
+    for arg in (sys.argv[1:] or ["sf", "an", "cs"]):   # "cs" or "cs:32" (scenarios per launch)
+        name = arg.split(":")[0]
         make, B, K, method = CASES[name]
+        if ":" in arg:
+            B = int(arg.split(":")[1])
         g = make()
         net = b200env.Network(g)
         for precision in ("fp32", "fp64"):
@@ -45,7 +48,7 @@ def main():
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / reps
             bytes_per = K * ((33 if precision == "fp32" else 65) * eng.E + 8 * eng.O * eng.N)
-            print(json.dumps({"network": name, "N": eng.N, "E": eng.E, "O": eng.O, "B": B, "K": K, "method": method,
+            print(json.dumps({"network": name, "kernel": eng.kernel_name, "cluster_env": os.environ.get("B200_CLUSTER", "auto"), "N": eng.N, "E": eng.E, "O": eng.O, "B": B, "K": K, "method": method,
                               "precision": precision, "ms": round(ms, 3), "assignments_per_s": round(B / ms * 1e3, 1),
                               "algorithmic_GBps": round(bytes_per * B / ms / 1e6, 2),
                               "median_gap": float(out["gap"].median())}), flush=True)
