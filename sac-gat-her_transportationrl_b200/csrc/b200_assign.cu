@@ -30,8 +30,8 @@ namespace {
 template <typename REAL>
 struct Cta {
     uint64_t *bar;
-    const int32_t *in_ptr, *in_src, *in_eid, *out_ptr, *out_dst;
-    int32_t *topo;
+    const uint16_t *in_ptr, *in_src, *in_eid, *out_ptr, *out_dst;   // 16-bit topology blob
+    uint16_t *topo;
     double *w;
     REAL *aux, *flow;
     double *red;
@@ -39,20 +39,22 @@ struct Cta {
     size_t warp_stride;
     int N, E;
     bool intq;   // link loads are accumulated as int32 in the aux array (exact, order-independent)
+    bool alias_cnt;   // pending-children counters live in the upper half of dist[] (see warp_offsets)
 
     // link load of link e as REAL, whatever the accumulation type
     __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
 
     __device__ void carve(unsigned char *smem, const Params &p, int warps)
     {
-        SmemLayout L = make_layout(p.N, p.E, p.topo_ints, warps, (int)sizeof(REAL));
+        alias_cnt = (sizeof(REAL) == 4 ? p.alias32 : p.alias64) != 0;
+        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt);
         bar = (uint64_t *)(smem + L.off_bar);
-        topo = (int32_t *)(smem + L.off_topo);
+        topo = (uint16_t *)(smem + L.off_topo);
         in_ptr = topo;
-        in_src = topo + p.off_in_src;
-        in_eid = topo + p.off_in_eid;
-        out_ptr = topo + p.off_out_ptr;
-        out_dst = topo + p.off_out_dst;
+        in_src = topo + p.o16_in_src;
+        in_eid = topo + p.o16_in_eid;
+        out_ptr = topo + p.o16_out_ptr;
+        out_dst = topo + p.o16_out_dst;
         intq = p.intq != 0;
         w = (double *)(smem + L.off_w);
         aux = (REAL *)(smem + L.off_aux);
@@ -64,7 +66,6 @@ struct Cta {
         E = p.E;
     }
     __device__ double *dist(int warp) const { return (double *)(warp_base + warp_stride * warp); }
-    __device__ uint16_t *pk(int warp) const { return (uint16_t *)(warp_base + warp_stride * warp + warp_offsets(N).pk); }
 
     // Stage the static topology into shared memory with one TMA bulk copy (UBLKCP).
     __device__ void stage_topology(const Params &p)
@@ -75,9 +76,9 @@ struct Cta {
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t bytes = (uint32_t)p.topo_ints * 4u;
+            const uint32_t bytes = (uint32_t)p.topo16_bytes;
             mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s(topo, p.topo, bytes, bar);
+            tma_bulk_g2s(topo, p.topo16, bytes, bar);
         }
         mbar_wait(bar, 0);
     }
@@ -123,7 +124,7 @@ template <typename REAL>
 __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp)
 {
     unsigned char *base = c.warp_base + c.warp_stride * warp;
-    const WarpOffsets W = warp_offsets(c.N);
+    const WarpOffsets W = warp_offsets(c.N, c.alias_cnt);
     WarpScratch s;
     s.dist = (double *)base;
     s.pk = (uint16_t *)(base + W.pk);
@@ -156,6 +157,12 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
     const int lane = threadIdx.x & 31, N = c.N;
     const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
     double *dist = s.dist;
+    // read-only topology / costs: __restrict__ tells the compiler that the 16-bit queue stores below
+    // cannot modify them (same element type -> no type-based disambiguation), so the loads of an
+    // unrolled step can be issued together
+    const uint16_t *__restrict__ in_ptr = c.in_ptr, *__restrict__ in_src = c.in_src, *__restrict__ out_ptr = c.out_ptr,
+                   *__restrict__ out_dst = c.out_dst;
+    const double *__restrict__ w = c.w;
     for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     uint16_t *cur = s.q0, *nxt = s.q1;
     int count;
@@ -170,17 +177,17 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                 const bool valid = base + lane < count;
                 const int u = valid ? (int)cur[base + lane] : 0;
                 const double du = valid ? dist[u] : 0.0;
-                const int j0 = valid ? c.out_ptr[u] : 0, j1 = valid ? c.out_ptr[u + 1] : 0;
+                const int j0 = valid ? out_ptr[u] : 0, j1 = valid ? out_ptr[u + 1] : 0;
                 for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
                     int xs[kLinkUnroll], ks[kLinkUnroll];
 #pragma unroll
-                    for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? c.out_dst[j0 + jb + i] : -1;
+                    for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? out_dst[j0 + jb + i] : -1;
 #pragma unroll
                     for (int i = 0; i < kLinkUnroll; ++i) ks[i] = xs[i] >= 0 ? (int)s.pk[xs[i]] : kNoPk;
 #pragma unroll
                     for (int i = 0; i < kLinkUnroll; ++i) {
-                        const bool child = ks[i] != kNoPk && c.in_src[ks[i]] == u;
-                        if (child) dist[xs[i]] = du + c.w[ks[i]];
+                        const bool child = ks[i] != kNoPk && in_src[ks[i]] == u;
+                        if (child) dist[xs[i]] = du + w[ks[i]];
                         const unsigned m = __ballot_sync(FULL, child);
                         if (child) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
                         ntail += __popc(m);
@@ -201,10 +208,10 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
     } else {
         for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
         __syncwarp();
-        const int o0 = c.out_ptr[origin];
-        count = c.out_ptr[origin + 1] - o0;
+        const int o0 = out_ptr[origin];
+        count = out_ptr[origin + 1] - o0;
         for (int j = lane; j < count; j += 32) {
-            const int x = c.out_dst[o0 + j];
+            const int x = out_dst[o0 + j];
             cur[j] = (uint16_t)x;
             atomicOr(&s.mask[x >> 5], 1u << (x & 31));
         }
@@ -222,15 +229,15 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
             if (valid) {
                 const double dv = dist[v];
                 double best = dv;
-                const int k0 = c.in_ptr[v], k1 = c.in_ptr[v + 1];
+                const int k0 = in_ptr[v], k1 = in_ptr[v + 1];
                 for (int kb = k0; kb < k1; kb += kLinkUnroll) {
                     int us[kLinkUnroll];
                     double ws[kLinkUnroll];
 #pragma unroll
                     for (int i = 0; i < kLinkUnroll; ++i) {
                         const bool ok = kb + i < k1;
-                        us[i] = ok ? c.in_src[kb + i] : v;
-                        ws[i] = ok ? c.w[kb + i] : B200_INF_F64;
+                        us[i] = ok ? in_src[kb + i] : v;
+                        ws[i] = ok ? w[kb + i] : B200_INF_F64;
                     }
 #pragma unroll
                     for (int i = 0; i < kLinkUnroll; ++i) {
@@ -241,12 +248,12 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                 improved = best < dv;
                 if (improved) dist[v] = best;
             }
-            const int j0 = improved ? c.out_ptr[v] : 0, j1 = improved ? c.out_ptr[v + 1] : 0;
+            const int j0 = improved ? out_ptr[v] : 0, j1 = improved ? out_ptr[v + 1] : 0;
             for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
                 int xs[kLinkUnroll];
                 bool fresh[kLinkUnroll];
 #pragma unroll
-                for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? c.out_dst[j0 + jb + i] : -1;
+                for (int i = 0; i < kLinkUnroll; ++i) xs[i] = j0 + jb + i < j1 ? out_dst[j0 + jb + i] : -1;
 #pragma unroll
                 for (int i = 0; i < kLinkUnroll; ++i) {
                     fresh[i] = false;
@@ -274,11 +281,11 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
         int bk = kNoPk, bu = -1;
         double bdu = B200_INF_F64;
         if (v != origin && dv < B200_INF_F64) {
-            const int k1 = c.in_ptr[v + 1];
-            for (int k = c.in_ptr[v]; k < k1; ++k) {
-                const int u = c.in_src[k];
+            const int k1 = in_ptr[v + 1];
+            for (int k = in_ptr[v]; k < k1; ++k) {
+                const int u = in_src[k];
                 const double du = dist[u];
-                if (du + c.w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
+                if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
                     bk = k; bu = u; bdu = du;
                 }
             }
@@ -302,6 +309,7 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
 {
     using QT = typename std::conditional<INTQ, int, REAL>::type;
     const int lane = threadIdx.x & 31, N = c.N;
+    const uint16_t *__restrict__ in_src = c.in_src, *__restrict__ in_eid = c.in_eid;
     QT *sacc = (QT *)s.dist;   // dist is dead once pk is chosen
     QT *auxq = (QT *)c.aux;
     const REAL *q = (const REAL *)p.od_q;
@@ -315,7 +323,7 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
     for (int v = lane; v < N; v += 32) {
         const int k = s.pk[v];
         if (k != kNoPk) {
-            const int u = c.in_src[k];
+            const int u = in_src[k];
             atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
         } else {
             un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
@@ -341,10 +349,10 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
             int u = 0;
             if (base + lane < count) {
                 const int v = cur[base + lane], k = s.pk[v];
-                u = c.in_src[k];
+                u = in_src[k];
                 const QT sv = sacc[v];
                 if (sv != (QT)0) {
-                    atomicAdd(&auxq[c.in_eid[k]], sv);
+                    atomicAdd(&auxq[in_eid[k]], sv);
                     atomicAdd(&sacc[u], sv);
                 }
                 const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
@@ -611,7 +619,7 @@ template <typename REAL, bool INTQ>
 __device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double *un_s, int *flag_s)
 {
     using QT = typename std::conditional<INTQ, int, REAL>::type;
-    constexpr int CH = 16;
+    constexpr int CH = 8;
     const unsigned C = cluster.num_blocks();
     QT *mine = (QT *)c.aux;
     double un = 0.0;
@@ -648,8 +656,11 @@ __device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double
 }
 
 // The fused path: K iterations of S1..S4 with every per-scenario array in shared memory.
-template <typename REAL>
-__global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
+// MINB = 2: at most 64 registers per thread, for networks small enough that several CTAs share an
+// SM (occupancy is what this latency-bound kernel lives on); MINB = 1: up to 128 registers when
+// shared memory allows only one CTA per SM anyway (Chicago-Sketch-size)
+template <typename REAL, int MINB>
+__global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     Cta<REAL> c;
@@ -719,14 +730,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32) assign_fused_kernel(Params p)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// subtree sums are 4-byte (int32 / float) -> the counters fit into the dead half of dist[]
+static int gen_alias(const b200_graph *g, int real_bytes)
+{
+    return (g->gen_intq || real_bytes == 4) && getenv("B200_NO_ALIAS") == nullptr;
+}
+
 Params base_params(const b200_graph *g, int B, int prec, double alpha, double beta)
 {
     Params p;
     memset(&p, 0, sizeof(p));
     p.N = g->N; p.E = g->E; p.O = g->O; p.topo_ints = g->topo_ints;
     p.off_in_src = g->off_in_src; p.off_in_eid = g->off_in_eid;
-    p.off_out_ptr = g->off_out_ptr; p.off_out_dst = g->off_out_dst;
+    p.topo16 = g->topo16; p.topo16_bytes = g->topo16_bytes; p.o16_in_src = g->o16_in_src; p.o16_in_eid = g->o16_in_eid;
+    p.o16_out_ptr = g->o16_out_ptr; p.o16_out_dst = g->o16_out_dst;
     p.intq = g->gen_intq; p.warm = g->warm_start;
+    p.alias32 = gen_alias(g, 4); p.alias64 = gen_alias(g, 8);
     p.topo = g->topo; p.row = g->row; p.origins = g->origins; p.od_ptr = g->od_ptr; p.od_dst = g->od_dst;
     p.t0_csc = g->t0_csc; p.cap0_csc = g->cap0_csc; p.t0 = g->t0; p.cap0 = g->cap0;
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
@@ -751,7 +770,7 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
     // Small networks: one CTA per scenario, the hardware block scheduler balances the tail and
     // re-staging a sub-8-KB topology is free.  Large networks: persistent CTAs, topology staged once.
     const int capacity = per_sm * g->num_sms;
-    int grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, capacity);
+    int grid = (g->topo16_bytes <= 5120) ? p.B : std::min(p.B, capacity);
     int cluster = 1;
     if (fused) {
         // Fewer scenarios than resident CTAs: split every scenario's origins over a thread-block
@@ -779,7 +798,7 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
                 grid = cluster * std::min(p.B, max_clusters);
             }
         }
-        if (cluster == 1) grid = ((size_t)g->topo_ints * 4 <= 8192) ? p.B : std::min(p.B, capacity);
+        if (cluster == 1) grid = (g->topo16_bytes <= 5120) ? p.B : std::min(p.B, capacity);
         // previous-iteration trees of the resident scenarios (the only allocation the library ever
         // makes after graph upload; it grows monotonically and is reused by later calls)
         const size_t need = (size_t)(grid / cluster) * g->O * g->N * sizeof(uint16_t);
@@ -809,6 +828,11 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
 
 }  // namespace
 
+static bool gen_alias_host(const b200_graph *g, int real_bytes)
+{
+    return (g->gen_intq || real_bytes == 4) && getenv("B200_NO_ALIAS") == nullptr;
+}
+
 // Warps per CTA: enough to spread the origins evenly, bounded by shared memory.
 int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
 {
@@ -820,16 +844,18 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
     // SM (shared memory: 227 KB per SM, 1 KB reserved per CTA), weighted by how evenly the origins
     // divide among the warps.  Ties go to fewer warps per CTA (more CTAs = more scenarios in flight).
     double best_score = -1.0;
+    const int forced = getenv("B200_WARPS") ? atoi(getenv("B200_WARPS")) : 0;   // tuning experiments
     for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-        SmemLayout L = make_layout(g->N, g->E, g->topo_ints, w, rb);
+        SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, rb, gen_alias_host(g, rb));
         if (L.total > kSmemLimit) break;
+        if (forced && w != forced) continue;
         const int O = std::max(g->O, 1);
         const double eff = (double)O / (double)(((O + w - 1) / w) * w);
         const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
         const double score = eff * w * std::max(ctas, 1);
         if (score > best_score + 1e-9) { best_score = score; best = w; }
     }
-    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo_ints, best, rb).total;
+    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo16_bytes, best, rb, gen_alias_host(g, rb)).total;
     return best;
 }
 
@@ -918,8 +944,14 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
         // Sioux-Falls class: one warp per scenario, lane = origin
         rc = b200_launch_small(g, p, prec, (cudaStream_t)stream);
     } else {
-        rc = prec == B200_F32 ? launch_cta_kernel(assign_fused_kernel<float>, g, prec, p, (cudaStream_t)stream, true)
-                              : launch_cta_kernel(assign_fused_kernel<double>, g, prec, p, (cudaStream_t)stream, true);
+        const size_t smem = prec == B200_F32 ? g->smem_f32 : g->smem_f64;
+        const bool one_cta = 2 * (smem + 1024) > 228 * 1024;   // shared memory admits a single CTA per SM
+        if (prec == B200_F32)
+            rc = one_cta ? launch_cta_kernel(assign_fused_kernel<float, 1>, g, prec, p, (cudaStream_t)stream, true)
+                         : launch_cta_kernel(assign_fused_kernel<float, 2>, g, prec, p, (cudaStream_t)stream, true);
+        else
+            rc = one_cta ? launch_cta_kernel(assign_fused_kernel<double, 1>, g, prec, p, (cudaStream_t)stream, true)
+                         : launch_cta_kernel(assign_fused_kernel<double, 2>, g, prec, p, (cudaStream_t)stream, true);
     }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;
     return rc;

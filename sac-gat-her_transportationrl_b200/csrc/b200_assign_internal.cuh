@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <type_traits>
 #include <vector>
@@ -26,37 +27,40 @@ __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t
 struct WarpOffsets {
     size_t pk, q0, q1, cnt, mask, tail, total;
 };
-__host__ __device__ inline WarpOffsets warp_offsets(int N)
+// alias_cnt: the subtree sums are 4-byte (int32 or float), so they fill only the lower half of the
+// dead dist[] array and the pending-children counters go into the upper half
+__host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt)
 {
     WarpOffsets W;
-    size_t o = align16((size_t)N * 8);
+    const size_t dist_bytes = align16((size_t)N * 8), cnt_bytes = align16((size_t)((N + 1) / 2) * 4);
+    size_t o = dist_bytes;
     W.pk = o;   o += align16((size_t)N * 2);
     W.q0 = o;   o += align16((size_t)N * 2);
     W.q1 = o;   o += align16((size_t)N * 2);
-    W.cnt = o;  o += align16((size_t)((N + 1) / 2) * 4);
+    if (alias_cnt && align16((size_t)N * 4) + cnt_bytes <= dist_bytes) W.cnt = align16((size_t)N * 4);
+    else { W.cnt = o; o += cnt_bytes; }
     W.mask = o; o += align16((size_t)((N + 31) / 32) * 4);
     W.tail = o; o += 16;
     W.total = o;
     return W;
 }
-__host__ __device__ inline size_t warp_scratch_bytes(int N) { return warp_offsets(N).total; }
 
 struct SmemLayout {
     size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_ints, int warps, int real_bytes)
+__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, int warps, int real_bytes, bool alias_cnt)
 {
     SmemLayout L;
     size_t o = 0;
     L.off_bar = o;  o += 16;
-    L.off_topo = o; o += align16((size_t)topo_ints * 4);
+    L.off_topo = o; o += align16((size_t)topo_bytes);
     L.off_w = o;    o += align16((size_t)E * 8);
     L.off_aux = o;  o += align16((size_t)E * real_bytes);
     L.off_flow = o; o += align16((size_t)E * real_bytes);
     L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
     L.off_warp = o;
-    L.warp_stride = warp_scratch_bytes(N);
+    L.warp_stride = warp_offsets(N, alias_cnt).total;
     L.total = o + L.warp_stride * warps;
     return L;
 }
@@ -70,7 +74,11 @@ struct SmallOffsets {
 struct Params {
     SmallOffsets so;
     // static network
-    int N, E, O, topo_ints, off_in_src, off_in_eid, off_out_ptr, off_out_dst;
+    int N, E, O, topo_ints, off_in_src, off_in_eid;
+    // general kernels: 16-bit topology blob, offsets in uint16 elements
+    const uint16_t *topo16;
+    int topo16_bytes, o16_in_src, o16_in_eid, o16_out_ptr, o16_out_dst;
+    int alias32, alias64;  // general kernel: counters aliased into dist[] (per precision; see warp_offsets)
     int warm;  // general kernel: warm-start shortest paths from the previous iteration's trees
     int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads
     const int32_t *topo, *row, *origins, *od_ptr, *od_dst;

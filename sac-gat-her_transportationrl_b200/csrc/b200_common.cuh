@@ -54,6 +54,10 @@ struct b200_graph {
     // appended for the general fused kernel: out-link CSR (out_ptr[N+1] | out_dst[E]), same blob so
     // one TMA copy stages everything; gen_intq = all demands are integers (total < 2^31)
     int off_out_ptr, off_out_dst, gen_intq;
+    // 16-bit copy of the whole blob for the general assignment kernels (half the shared memory);
+    // offsets in uint16 elements, every array padded to 16 bytes
+    uint16_t *topo16;
+    int topo16_bytes, o16_in_src, o16_in_eid, o16_out_ptr, o16_out_dst;
     // general fused kernel: previous-iteration trees, u16 [resident CTAs][O][N], grown on demand
     uint16_t *tree_ws;
     size_t tree_ws_bytes;

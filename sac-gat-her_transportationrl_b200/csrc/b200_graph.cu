@@ -157,6 +157,23 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     }
     int rc;
     if ((rc = upload(&g->topo, blob))) return rc;
+    if (N < 65535 && E < 65535) {
+        auto pad8 = [](int x) { return (x + 7) & ~7; };
+        g->o16_in_src = pad8(N + 1);
+        g->o16_in_eid = g->o16_in_src + pad8(E);
+        g->o16_out_ptr = g->o16_in_eid + pad8(E);
+        g->o16_out_dst = g->o16_out_ptr + pad8(N + 1);
+        const int total16 = g->o16_out_dst + pad8(E);
+        std::vector<uint16_t> b16(total16, 0);
+        for (int v = 0; v <= N; ++v) { b16[v] = (uint16_t)in_ptr[v]; b16[g->o16_out_ptr + v] = (uint16_t)out_ptr[v]; }
+        for (int k = 0; k < E; ++k) {
+            b16[g->o16_in_src + k] = (uint16_t)in_src[k];
+            b16[g->o16_in_eid + k] = (uint16_t)in_eid[k];
+            b16[g->o16_out_dst + k] = (uint16_t)out_dst[k];
+        }
+        g->topo16_bytes = total16 * 2;
+        if ((rc = upload(&g->topo16, b16))) return rc;
+    }
     std::vector<int32_t> vrow(row, row + E), vcol(col, col + E);
     std::vector<float> vt0(t0, t0 + E), vcap(cap0, cap0 + E), t0c(E), capc(E);
     for (int k = 0; k < E; ++k) { t0c[k] = t0[in_eid[k]]; capc[k] = cap0[in_eid[k]]; }
@@ -191,7 +208,7 @@ extern "C" int b200_graph_destroy(b200_graph *g)
     void *ptrs[] = {g->topo, g->row, g->col, g->t0, g->cap0, g->t0_csc, g->cap0_csc, g->origins, g->origin_slot,
                     g->od_ptr, g->od_dst, g->od_q64, g->od_q32, g->out_ptr, g->out_dst, g->out_eid,
                     g->small_blob32, g->small_blob64, g->small_blob_i32, g->small_eid, g->small_wpos,
-                    g->tree_ws, g->st_t0, g->st_cap0, g->st_eid, g->st_wpos, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
+                    g->tree_ws, g->topo16, g->st_t0, g->st_cap0, g->st_eid, g->st_wpos, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     free(g->origins_host);
