@@ -297,6 +297,7 @@ def run_ours(args) -> None:
     gap_med = float(env.gap.median().item())
     tstt_chk = float(env.tstt.sum().item())
 
+    other = None if args.no_extra else measure_other_configs(b200env, torch, dist, dev, rank, world, measured_peak()[0])
     if rank == 0:
         peak, peak_src = measured_peak()
         kern_s = statistics.mean(kern_ms) / 1e3
@@ -320,6 +321,7 @@ def run_ours(args) -> None:
                                  "binding limit is warp-instruction issue (DESIGN.md section 4)"},
             "quality": {"median_relative_gap_at_K": gap_med, "tstt_checksum": tstt_chk},
         }
+        line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1
             # ~0.1 s per assignment per core -> 100 per process is a 10-20 s bounded sample
@@ -330,6 +332,51 @@ def run_ours(args) -> None:
         dist.destroy_process_group()
 
 
+def measure_other_configs(b200env, torch, dist, dev, rank: int, world: int, peak: float) -> dict:
+    """BASELINE.json configs[2] and [3] - the synthetic Anaheim-size and Chicago-Sketch-size networks -
+    reported next to the headline line (informational: they are parity-test cases, not the metric).
+    The named scenario counts are TOTALS, sharded over the ranks (strong scaling, no collective);
+    time = max over ranks of the CUDA-event time of one fused launch (cold start, K = 20)."""
+    out = {}
+    cases = (("anaheim_size_fw_1024", lambda: b200env.synthetic.anaheim_size(0), 1024, "fw"),
+             ("chicago_sketch_size_msa_256", lambda: b200env.synthetic.chicago_sketch_size(0), 256, "msa"))
+    for name, make, total, method in cases:
+        eng = b200env.AssignmentEngine(b200env.Network(make()), dev, "fp32")
+        lo, hi = total * rank // world, total * (rank + 1) // world
+        rng = np.random.default_rng(1234)
+        masks = np.zeros((total, eng.E), np.uint8)
+        k = max(1, int(eng.E * 0.3))
+        for b in range(total):
+            masks[b, rng.choice(eng.E, k, replace=False)] = 1
+        dmg = torch.from_numpy(masks[lo:hi]).to(dev)
+        flow = torch.zeros((hi - lo, eng.E), dtype=eng.real, device=dev)
+        eng.assign(dmg, flow, ASSIGN_ITERS, method)
+        reps, ms = 3, []
+        for _ in range(reps):
+            flow.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+            s.record()
+            res = eng.assign(dmg, flow, ASSIGN_ITERS, method)
+            e.record()
+            torch.cuda.synchronize(dev)
+            t = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms.append(float(t.item()))
+        best = min(ms)
+        bytes_per = ASSIGN_ITERS * (33 * eng.E + 8 * eng.O * eng.N)
+        out[name] = {"assignments_per_s": total / best * 1e3, "ms_per_launch": best, "scenarios_total": total,
+                     "scenarios_per_gpu": hi - lo, "method": method, "assignment_iters": ASSIGN_ITERS,
+                     "nodes": eng.N, "links": eng.E, "origins": eng.O, "kernel": eng.kernel_name, "scaling": "strong",
+                     "roofline_frac_per_gpu": bytes_per * (hi - lo) / (best / 1e3) / 1e9 / peak,
+                     "median_relative_gap_at_K": float(res["gap"].median().item())}
+        del eng
+    return out
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,6 +384,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the informational Anaheim / Chicago-Sketch-size figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
