@@ -44,10 +44,10 @@ struct Cta {
     // link load of link e as REAL, whatever the accumulation type
     __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
 
-    __device__ void carve(unsigned char *smem, const Params &p, int warps)
+    __device__ void carve(unsigned char *smem, const Params &p, int warps, int slots = 1)
     {
         alias_cnt = (sizeof(REAL) == 4 ? p.alias32 : p.alias64) != 0;
-        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt);
+        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt, slots);
         bar = (uint64_t *)(smem + L.off_bar);
         topo = (uint16_t *)(smem + L.off_topo);
         in_ptr = topo;
@@ -120,11 +120,13 @@ struct WarpScratch {
     uint32_t *cntw, *mask;
     int *tail;
 };
+// Scratch of origin slot `slot` of a warp (a warp works on 32 / G origins at once, see below).
 template <typename REAL>
-__device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp)
+__device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp, int slot = 0, int slots = 1)
 {
-    unsigned char *base = c.warp_base + c.warp_stride * warp;
     const WarpOffsets W = warp_offsets(c.N, c.alias_cnt);
+    unsigned char *base = c.warp_base + c.warp_stride * warp + W.total * slot;
+    (void)slots;
     WarpScratch s;
     s.dist = (double *)base;
     s.pk = (uint16_t *)(base + W.pk);
@@ -141,41 +143,52 @@ __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp
 // after one of its in-neighbours improved; the "queued" bit of a node is cleared before its
 // in-neighbours are read, so an improvement that lands after the read re-queues the node for the
 // next round.  Rounds <= longest shortest path in hops.
+//
+// SUB-WARP GROUPS: a group of G lanes (G = 8, 16 or 32) owns one origin, so a warp advances 32 / G
+// origins in lock step.  On networks with narrow frontiers (a handful of nodes per round) a full
+// warp per origin wastes most lanes of every instruction, and the kernel is issue-bound once enough
+// warps are resident; with G = 8 the same instruction stream serves four origins.  All control flow
+// is warp-uniform (loops run while ANY group has work), group-local quantities are derived from
+// ballots masked with the group's lane mask.  `origin < 0` marks an idle group.
+//
 // Warm start (tree != nullptr: this origin's tree of the previous iteration, in-link slot per node):
 // the old tree is re-evaluated top-down under the new costs - every label is then the length of a
 // real path, i.e. a valid upper bound - and ALL nodes are queued once, so the first round is a
 // full verification pass and later rounds only follow actual changes.  The fixed point, and with
 // it the result, is the same as from a cold start.
-// Queue tails live in a warp-uniform register: new entries are placed by ballot + popcount, the
+// Queue tails live in a group-uniform register: new entries are placed by ballot + popcount, the
 // only shared-memory atomics are the "already queued" bits.  Link loops are unrolled by kLinkUnroll
 // so the dependent shared-memory loads of one step are issued together.
 constexpr int kLinkUnroll = 4;
 
-template <typename REAL>
+template <typename REAL, int G>
 __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, const uint16_t *tree = nullptr)
 {
-    const int lane = threadIdx.x & 31, N = c.N;
-    const unsigned FULL = 0xffffffffu, lt = (1u << lane) - 1u;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), N = c.N;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane - gl));
+    const unsigned lt = ((1u << gl) - 1u) << (lane - gl);   // lower lanes of my group
+    const bool live = origin >= 0;
     double *dist = s.dist;
-    // read-only topology / costs: __restrict__ tells the compiler that the 16-bit queue stores below
-    // cannot modify them (same element type -> no type-based disambiguation), so the loads of an
-    // unrolled step can be issued together
     const uint16_t *__restrict__ in_ptr = c.in_ptr, *__restrict__ in_src = c.in_src, *__restrict__ out_ptr = c.out_ptr,
                    *__restrict__ out_dst = c.out_dst;
     const double *__restrict__ w = c.w;
-    for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
+    if (live)
+        for (int v = gl; v < N; v += G) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     uint16_t *cur = s.q0, *nxt = s.q1;
-    int count;
-    if (tree) {
-        for (int v = lane; v < N; v += 32) s.pk[v] = tree[v];
-        if (lane == 0) cur[0] = (uint16_t)origin;
+    int count = 0;
+    if (tree) {   // warp-uniform (the iteration index decides)
+        if (live) {
+            for (int v = gl; v < N; v += G) s.pk[v] = tree[v];
+            if (gl == 0) cur[0] = (uint16_t)origin;
+            count = 1;
+        }
         __syncwarp();
-        count = 1;
-        while (count > 0) {   // breadth-first over the old tree's children
+        while (__any_sync(FULL, count > 0)) {   // breadth-first over the old tree's children
             int ntail = 0;
-            for (int base = 0; base < count; base += 32) {
-                const bool valid = base + lane < count;
-                const int u = valid ? (int)cur[base + lane] : 0;
+            for (int base = 0; __any_sync(FULL, base < count); base += G) {
+                const bool valid = base + gl < count;
+                const int u = valid ? (int)cur[base + gl] : 0;
                 const double du = valid ? dist[u] : 0.0;
                 const int j0 = valid ? out_ptr[u] : 0, j1 = valid ? out_ptr[u + 1] : 0;
                 for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
@@ -188,7 +201,7 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                     for (int i = 0; i < kLinkUnroll; ++i) {
                         const bool child = ks[i] != kNoPk && in_src[ks[i]] == u;
                         if (child) dist[xs[i]] = du + w[ks[i]];
-                        const unsigned m = __ballot_sync(FULL, child);
+                        const unsigned m = __ballot_sync(FULL, child) & gmask;
                         if (child) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
                         ntail += __popc(m);
                     }
@@ -199,30 +212,35 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
             uint16_t *t = cur; cur = nxt; nxt = t;
         }
         // queue every node but the origin
-        for (int v = lane; v < N; v += 32)
-            if (v != origin) cur[v - (v > origin ? 1 : 0)] = (uint16_t)v;
-        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0xffffffffu;
-        count = N - 1;
+        if (live) {
+            for (int v = gl; v < N; v += G)
+                if (v != origin) cur[v - (v > origin ? 1 : 0)] = (uint16_t)v;
+            for (int i = gl; i < (N + 31) / 32; i += G) s.mask[i] = 0xffffffffu;
+            count = N - 1;
+        }
         __syncwarp();
-        if (lane == 0) atomicAnd(&s.mask[origin >> 5], ~(1u << (origin & 31)));
+        if (live && gl == 0) atomicAnd(&s.mask[origin >> 5], ~(1u << (origin & 31)));
     } else {
-        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
+        if (live)
+            for (int i = gl; i < (N + 31) / 32; i += G) s.mask[i] = 0u;
         __syncwarp();
-        const int o0 = out_ptr[origin];
-        count = out_ptr[origin + 1] - o0;
-        for (int j = lane; j < count; j += 32) {
-            const int x = out_dst[o0 + j];
-            cur[j] = (uint16_t)x;
-            atomicOr(&s.mask[x >> 5], 1u << (x & 31));
+        if (live) {
+            const int o0 = out_ptr[origin];
+            count = out_ptr[origin + 1] - o0;
+            for (int j = gl; j < count; j += G) {
+                const int x = out_dst[o0 + j];
+                cur[j] = (uint16_t)x;
+                atomicOr(&s.mask[x >> 5], 1u << (x & 31));
+            }
         }
     }
     __syncwarp();
     int rounds = 0, capped = 0;
-    while (count > 0) {
+    while (__any_sync(FULL, count > 0)) {
         int ntail = 0;
-        for (int base = 0; base < count; base += 32) {
-            const bool valid = base + lane < count;
-            const int v = valid ? (int)cur[base + lane] : 0;
+        for (int base = 0; __any_sync(FULL, base < count); base += G) {
+            const bool valid = base + gl < count;
+            const int v = valid ? (int)cur[base + gl] : 0;
             if (valid) atomicAnd(&s.mask[v >> 5], ~(1u << (v & 31)));
             __syncwarp();
             bool improved = false;
@@ -264,7 +282,7 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                 }
 #pragma unroll
                 for (int i = 0; i < kLinkUnroll; ++i) {
-                    const unsigned m = __ballot_sync(FULL, fresh[i]);
+                    const unsigned m = __ballot_sync(FULL, fresh[i]) & gmask;
                     if (fresh[i]) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
                     ntail += __popc(m);
                 }
@@ -273,82 +291,93 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
         }
         count = ntail;
         uint16_t *t = cur; cur = nxt; nxt = t;
-        if (++rounds > N + 1) { capped = 1; break; }
+        if (++rounds > N + 1) { capped = count > 0; break; }
     }
     // predecessor: tight in-link with the smallest dist[u], then the largest u
-    for (int v = lane; v < N; v += 32) {
-        const double dv = dist[v];
-        int bk = kNoPk, bu = -1;
-        double bdu = B200_INF_F64;
-        if (v != origin && dv < B200_INF_F64) {
-            const int k1 = in_ptr[v + 1];
-            for (int k = in_ptr[v]; k < k1; ++k) {
-                const int u = in_src[k];
-                const double du = dist[u];
-                if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
-                    bk = k; bu = u; bdu = du;
+    if (live) {
+        for (int v = gl; v < N; v += G) {
+            const double dv = dist[v];
+            int bk = kNoPk, bu = -1;
+            double bdu = B200_INF_F64;
+            if (v != origin && dv < B200_INF_F64) {
+                const int k1 = in_ptr[v + 1];
+                for (int k = in_ptr[v]; k < k1; ++k) {
+                    const int u = in_src[k];
+                    const double du = dist[u];
+                    if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
+                        bk = k; bu = u; bdu = du;
+                    }
                 }
             }
+            s.pk[v] = (uint16_t)bk;
         }
-        s.pk[v] = (uint16_t)bk;
     }
     __syncwarp();
     return capped;
 }
 
 // ---------------------------------------------------------------------------------------------
-// S3: one warp, one origin - subtree demand sums, leaves first (Kahn), link loads into c.aux
+// S3: one group of lanes, one origin - subtree demand sums, leaves first (Kahn), link loads into c.aux
 // ---------------------------------------------------------------------------------------------
 // Every tree link is handled once: a node whose children are all done adds its subtree sum to
 // its in-link and to its parent.  The frontier of "ready" nodes is a queue; pending-children
 // counters are 16-bit, two per 32-bit word, updated with 32-bit shared-memory atomics.
 // INTQ: sums are int32 (exact, order-independent); otherwise REAL atomics (order-dependent in the
 // last bits, like any parallel sum).  Returns this lane's share of the unassigned demand.
-template <typename REAL, bool INTQ>
+template <typename REAL, bool INTQ, int G>
 __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
     using QT = typename std::conditional<INTQ, int, REAL>::type;
-    const int lane = threadIdx.x & 31, N = c.N;
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), N = c.N;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane - gl));
+    const unsigned lt = ((1u << gl) - 1u) << (lane - gl);
+    const bool live = origin >= 0;
     const uint16_t *__restrict__ in_src = c.in_src, *__restrict__ in_eid = c.in_eid;
     QT *sacc = (QT *)s.dist;   // dist is dead once pk is chosen
     QT *auxq = (QT *)c.aux;
     const REAL *q = (const REAL *)p.od_q;
-    for (int v = lane; v < N; v += 32) sacc[v] = 0;
-    for (int i = lane; i < (N + 1) / 2; i += 32) s.cntw[i] = 0u;
+    if (live) {
+        for (int v = gl; v < N; v += G) sacc[v] = 0;
+        for (int i = gl; i < (N + 1) / 2; i += G) s.cntw[i] = 0u;
+    }
     __syncwarp();
-    const int jd1 = __ldg(p.od_ptr + slot + 1);
-    for (int j = __ldg(p.od_ptr + slot) + lane; j < jd1; j += 32) sacc[__ldg(p.od_dst + j)] = (QT)q[j];
+    if (live) {
+        const int jd1 = __ldg(p.od_ptr + slot + 1);
+        for (int j = __ldg(p.od_ptr + slot) + gl; j < jd1; j += G) sacc[__ldg(p.od_dst + j)] = (QT)q[j];
+    }
     __syncwarp();
     double un = 0.0;
-    for (int v = lane; v < N; v += 32) {
-        const int k = s.pk[v];
-        if (k != kNoPk) {
-            const int u = in_src[k];
-            atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
-        } else {
-            un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
+    if (live) {
+        for (int v = gl; v < N; v += G) {
+            const int k = s.pk[v];
+            if (k != kNoPk) {
+                const int u = in_src[k];
+                atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
+            } else {
+                un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
+            }
         }
     }
     __syncwarp();
     uint16_t *cur = s.q0, *nxt = s.q1;
     int count = 0;
-    for (int v0 = 0; v0 < N; v0 += 32) {
-        const int v = v0 + lane;
+    for (int v0 = 0; v0 < N; v0 += G) {
+        const int v = v0 + gl;
         bool leaf = false;
-        if (v < N && s.pk[v] != kNoPk) leaf = ((s.cntw[v >> 1] >> ((v & 1) * 16)) & 0xffffu) == 0u;
-        const unsigned m = __ballot_sync(0xffffffffu, leaf);
-        if (leaf) cur[count + __popc(m & ((1u << lane) - 1u))] = (uint16_t)v;
+        if (live && v < N && s.pk[v] != kNoPk) leaf = ((s.cntw[v >> 1] >> ((v & 1) * 16)) & 0xffffu) == 0u;
+        const unsigned m = __ballot_sync(FULL, leaf) & gmask;
+        if (leaf) cur[count + __popc(m & lt)] = (uint16_t)v;
         count += __popc(m);
     }
     __syncwarp();
-    const unsigned lt = (1u << lane) - 1u;
-    while (count > 0) {
+    while (__any_sync(FULL, count > 0)) {
         int ntail = 0;
-        for (int base = 0; base < count; base += 32) {
+        for (int base = 0; __any_sync(FULL, base < count); base += G) {
             bool ready = false;
             int u = 0;
-            if (base + lane < count) {
-                const int v = cur[base + lane], k = s.pk[v];
+            if (base + gl < count) {
+                const int v = cur[base + gl], k = s.pk[v];
                 u = in_src[k];
                 const QT sv = sacc[v];
                 if (sv != (QT)0) {
@@ -358,7 +387,7 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
                 const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
                 ready = ((old >> ((u & 1) * 16)) & 0xffffu) == 1u && u != origin;   // that was the last child
             }
-            const unsigned m = __ballot_sync(0xffffffffu, ready);
+            const unsigned m = __ballot_sync(FULL, ready) & gmask;
             if (ready) nxt[ntail + __popc(m & lt)] = (uint16_t)u;
             ntail += __popc(m);
         }
@@ -369,10 +398,10 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
     return un;
 }
 
-template <typename REAL>
+template <typename REAL, int G>
 __device__ __forceinline__ double warp_aon(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
-    return c.intq ? warp_aon_peel<REAL, true>(c, p, slot, origin, s) : warp_aon_peel<REAL, false>(c, p, slot, origin, s);
+    return c.intq ? warp_aon_peel<REAL, true, G>(c, p, slot, origin, s) : warp_aon_peel<REAL, false, G>(c, p, slot, origin, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,7 +548,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) sssp_kernel(Params p)
         for (int s = warp; s < p.O; s += W) {
             const int o = __ldg(p.origins + s);
             const WarpScratch ws = warp_scratch(c, warp);
-            capped |= warp_sssp<REAL>(c, o, ws);
+            capped |= warp_sssp<REAL, 32>(c, o, ws);
             const size_t base = ((size_t)b * p.O + s) * p.N;
             for (int v = lane; v < p.N; v += 32) {
                 const int k = ws.pk[v];
@@ -556,7 +585,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) aon_kernel(Params p)
             const int32_t *pe = p.pedge_in + ((size_t)b * p.O + s) * p.N;
             for (int v = lane; v < p.N; v += 32) { const int e = pe[v]; ws.pk[v] = (uint16_t)(e < 0 ? kNoPk : slot_of[e]); }
             __syncwarp();
-            un += warp_aon<REAL>(c, p, s, o, ws);
+            un += warp_aon<REAL, 32>(c, p, s, o, ws);
             __syncwarp();
         }
         un = warp_sum_f64(un);
@@ -659,7 +688,7 @@ __device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double
 // MINB = 2: at most 64 registers per thread, for networks small enough that several CTAs share an
 // SM (occupancy is what this latency-bound kernel lives on); MINB = 1: up to 128 registers when
 // shared memory allows only one CTA per SM anyway (Chicago-Sketch-size)
-template <typename REAL, int MINB>
+template <typename REAL, int MINB, int G>
 __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -667,7 +696,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    c.carve(smem, p, W);
+    constexpr int OPW = 32 / G;          // origins per warp
+    const int group = lane / G, gl = lane & (G - 1);
+    c.carve(smem, p, W, OPW);
     c.stage_topology(p);
     double *un_s = &c.red[kMaxWarps * 2];
     int *flag_s = (int *)&c.red[kMaxWarps * 2 + 1];
@@ -689,18 +720,20 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
             __syncthreads();   // (neighbours finished pulling last iteration's loads before its last cluster barrier)
             double un = 0.0;
             int capped = 0;
-            for (int s = rank * W + warp; s < p.O; s += C * W) {
-                const int o = __ldg(p.origins + s);
-                const WarpScratch ws = warp_scratch(c, warp);
-                uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + s) * p.N;
-                capped |= warp_sssp<REAL>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
-                for (int v = lane; v < p.N; v += 32) tree[v] = ws.pk[v];   // next iteration's warm start
-                un += warp_aon<REAL>(c, p, s, o, ws);
+            for (int s0 = (rank * W + warp) * OPW; s0 < p.O; s0 += C * W * OPW) {
+                const int s = s0 + group;                     // this lane group's origin slot
+                const int o = s < p.O ? __ldg(p.origins + s) : -1;
+                const WarpScratch ws = warp_scratch(c, warp, group, OPW);
+                uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + (s < p.O ? s : 0)) * p.N;
+                capped |= warp_sssp<REAL, G>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
+                if (o >= 0 && p.warm)
+                    for (int v = gl; v < p.N; v += G) tree[v] = ws.pk[v];   // next iteration's warm start
+                un += warp_aon<REAL, G>(c, p, s, o, ws);
                 __syncwarp();
             }
             un = warp_sum_f64(un);
             if (lane == 0 && un != 0.0) atomicAdd(un_s, un);
-            if (capped && lane == 0) flag_s[1] = 1;
+            if (__any_sync(0xffffffffu, capped) && lane == 0) flag_s[1] = 1;
             __syncthreads();
             if (C > 1) {
                 cluster.sync();   // every CTA's partial loads are complete
@@ -778,7 +811,7 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
         // CTA per scenario (its direction scratch lives in the caller's [B][E] array).
         if (g->cluster_limit != 1 && p.method != B200_CFW) {
             const int want = std::min({8, g->cluster_limit > 0 ? g->cluster_limit : 8, capacity / std::max(p.B, 1),
-                                       (g->O + warps - 1) / warps});
+                                       (g->O + warps * std::max(p.slots, 1) - 1) / (warps * std::max(p.slots, 1))});
             while (cluster * 2 <= want) cluster *= 2;
         }
         if (cluster > 1) {
@@ -845,17 +878,18 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
     // divide among the warps.  Ties go to fewer warps per CTA (more CTAs = more scenarios in flight).
     double best_score = -1.0;
     const int forced = getenv("B200_WARPS") ? atoi(getenv("B200_WARPS")) : 0;   // tuning experiments
+    const int slots = 32 / std::max(g->group_lanes, 8);   // origins per warp of the FUSED kernel
     for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-        SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, rb, gen_alias_host(g, rb));
+        SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, rb, gen_alias_host(g, rb), slots);
         if (L.total > kSmemLimit) break;
         if (forced && w != forced) continue;
-        const int O = std::max(g->O, 1);
-        const double eff = (double)O / (double)(((O + w - 1) / w) * w);
+        const int O = std::max(g->O, 1), batch = w * slots;
+        const double eff = (double)O / (double)(((O + batch - 1) / batch) * batch);
         const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
-        const double score = eff * w * std::max(ctas, 1);
+        const double score = eff * batch * std::max(ctas, 1);
         if (score > best_score + 1e-9) { best_score = score; best = w; }
     }
-    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo16_bytes, best, rb, gen_alias_host(g, rb)).total;
+    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo16_bytes, best, rb, gen_alias_host(g, rb), slots).total;
     return best;
 }
 
@@ -946,12 +980,13 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
     } else {
         const size_t smem = prec == B200_F32 ? g->smem_f32 : g->smem_f64;
         const bool one_cta = 2 * (smem + 1024) > 228 * 1024;   // shared memory admits a single CTA per SM
-        if (prec == B200_F32)
-            rc = one_cta ? launch_cta_kernel(assign_fused_kernel<float, 1>, g, prec, p, (cudaStream_t)stream, true)
-                         : launch_cta_kernel(assign_fused_kernel<float, 2>, g, prec, p, (cudaStream_t)stream, true);
-        else
-            rc = one_cta ? launch_cta_kernel(assign_fused_kernel<double, 1>, g, prec, p, (cudaStream_t)stream, true)
-                         : launch_cta_kernel(assign_fused_kernel<double, 2>, g, prec, p, (cudaStream_t)stream, true);
+        cudaStream_t st = (cudaStream_t)stream;
+        p.slots = 32 / g->group_lanes;
+#define B200_LAUNCH_FUSED(REAL, G)                                                              \
+    (one_cta ? launch_cta_kernel(assign_fused_kernel<REAL, 1, G>, g, prec, p, st, true)          \
+             : launch_cta_kernel(assign_fused_kernel<REAL, 2, G>, g, prec, p, st, true))
+        rc = prec == B200_F32 ? B200_LAUNCH_FUSED(float, 32) : B200_LAUNCH_FUSED(double, 32);   // see group_lanes
+#undef B200_LAUNCH_FUSED
     }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;
     return rc;

@@ -49,7 +49,8 @@ struct SmemLayout {
     size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
 };
 
-__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, int warps, int real_bytes, bool alias_cnt)
+__host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, int warps, int real_bytes, bool alias_cnt,
+                                                  int slots = 1)
 {
     SmemLayout L;
     size_t o = 0;
@@ -60,7 +61,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, 
     L.off_flow = o; o += align16((size_t)E * real_bytes);
     L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
     L.off_warp = o;
-    L.warp_stride = warp_offsets(N, alias_cnt).total;
+    L.warp_stride = warp_offsets(N, alias_cnt).total * slots;   // slots = origins a warp works on at once
     L.total = o + L.warp_stride * warps;
     return L;
 }
@@ -78,6 +79,7 @@ struct Params {
     // general kernels: 16-bit topology blob, offsets in uint16 elements
     const uint16_t *topo16;
     int topo16_bytes, o16_in_src, o16_in_eid, o16_out_ptr, o16_out_dst;
+    int slots;  // general fused kernel: origins per warp (32 / lanes per origin group)
     int alias32, alias64;  // general kernel: counters aliased into dist[] (per precision; see warp_offsets)
     int warm;  // general kernel: warm-start shortest paths from the previous iteration's trees
     int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads

@@ -62,6 +62,7 @@ struct b200_graph {
     uint16_t *tree_ws;
     size_t tree_ws_bytes;
     int warm_start;   // 0 disables the warm start (env B200_NO_WARM, A/B measurements)
+    int group_lanes;     // lanes per origin group in the general fused kernel (8 or 32; env B200_GROUP)
     int cluster_limit;   // max thread-block cluster size of the general kernel (env B200_CLUSTER; 1 = off, 0 = auto)
     int last_cluster;    // cluster size of the last fused launch (tests / tools)
     // per-link attributes, TNTP order

@@ -131,6 +131,11 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     if (getenv("B200_NO_WARM")) g->warm_start = 0;
     if (getenv("B200_WARM")) g->warm_start = 1;
     g->cluster_limit = getenv("B200_CLUSTER") ? atoi(getenv("B200_CLUSTER")) : 0;
+    // Lanes per origin.  The device code supports sub-warp groups (8 lanes per origin, four origins
+    // per warp), but measured on the Anaheim-size network that is 3x SLOWER than a warp per origin:
+    // the kernel is bound by the latency of each origin's dependent chain, and the O(N) passes
+    // (initialisation, predecessor selection, leaf scan) get four times as many steps.
+    g->group_lanes = 32;
     g->N = N; g->E = E; g->O = O; g->num_od = num_od; g->max_in_deg = max_in; g->total_demand = total;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
