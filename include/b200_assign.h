@@ -100,6 +100,11 @@ int b200_assign_launches(const b200_graph *g);
 /* Which fused kernel b200_assign dispatches to for this network ("assign_static_kernel",
  * "assign_small_kernel" or "assign_fused_kernel"; static string). */
 const char *b200_assign_kernel_name(const b200_graph *g);
+/* Register a network-specialised kernel compiled on demand for one small topology (a shared object
+ * built from csrc/b200_static_plugin.cu; see _native.specialize).  Networks uploaded AFTERWARDS whose
+ * link list equals the plugin's topology take its straight-line kernel, like Sioux Falls takes the
+ * built-in one.  Not in the reference (it has a single generic Python path). */
+int b200_register_static_plugin(const char *path);
 
 /* S5 - get_state features (reference :751-819).  Inputs: flow real [B][E], dmg/goal uint8 [B][E],
  * tstt f64 [B].  Outputs fp32: node_feat [B][N][4], edge_feat [B][E][6]; capacity_damage is the

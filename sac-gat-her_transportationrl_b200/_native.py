@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
     "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
-    "b200_assign_launches", "b200_assign_kernel_name", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_assign_launches", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
     "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
 ]
 
@@ -70,7 +70,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps = {"b200_assign.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
             "b200_assign_small.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", api],
             "b200_assign_static.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_static.cuh",
-                                      "b200_topo_siouxfalls.h", api]}
+                                      "b200_topo_siouxfalls.h", api],
+            "b200_graph.cu": ["b200_common.cuh", api], "b200_env.cu": ["b200_common.cuh", api],
+            "b200_gat.cu": ["b200_common.cuh", api]}
     procs = []
     for src in SOURCES:
         obj, path = _obj_path(src), os.path.join(CSRC, src)
@@ -86,7 +88,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         log.append(err)
         if proc.returncode != 0:
             raise NativeLibraryError(f"nvcc failed on {src}:\n" + err[-4000:])
-    res = subprocess.run([_nvcc(), "-shared", "-o", LIB_PATH] + [_obj_path(s) for s in SOURCES],
+    res = subprocess.run([_nvcc(), "-shared", "-o", LIB_PATH] + [_obj_path(s) for s in SOURCES] + ["-ldl"],
                          capture_output=True, text=True)
     if res.returncode != 0:
         raise NativeLibraryError("link failed:\n" + res.stderr[-4000:])
@@ -116,6 +118,7 @@ def _declare(lib) -> None:
     lib.b200_assign.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp]
     lib.b200_assign_launches.argtypes = [_vp]
     lib.b200_assign_kernel_name.argtypes = [_vp]
+    lib.b200_register_static_plugin.argtypes = [C.c_char_p]
     lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]
     lib.b200_apply_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
     lib.b200_reward_done.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp]
@@ -138,6 +141,57 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _declare(_lib)
     return _lib
+
+
+# ---------------------------------------------------------------------------------------------
+# on-demand network-specialised kernels
+# ---------------------------------------------------------------------------------------------
+SPECIALIZE_MAX_NODES, SPECIALIZE_MAX_LINKS = 32, 160  # distance labels live in registers: 2 per node
+
+
+def specialize(num_nodes: int, row, col, t0, origins, verbose: bool = False) -> str:
+    """Compile (once, cached in csrc/_jit/) and register the straight-line assignment kernel for one
+    small topology: the same hand-written template Sioux Falls uses (csrc/b200_assign_static.cuh),
+    instantiated for a generated topology header.  Networks uploaded afterwards with this link list
+    dispatch to it.  Takes about a minute of nvcc the first time; returns the plugin path."""
+    import hashlib
+
+    import numpy as np
+
+    from . import codegen
+
+    row = np.ascontiguousarray(row, dtype=np.int64)
+    col = np.ascontiguousarray(col, dtype=np.int64)
+    E = int(row.shape[0])
+    if num_nodes > SPECIALIZE_MAX_NODES or E > SPECIALIZE_MAX_LINKS or len(origins) > 32 or len(origins) < 1:
+        raise ValueError(f"network too large for a specialised kernel (N <= {SPECIALIZE_MAX_NODES}, "
+                         f"E <= {SPECIALIZE_MAX_LINKS}, origins <= 32)")
+    h = hashlib.sha1()
+    h.update(np.int64(num_nodes).tobytes() + row.tobytes() + col.tobytes())
+    for dep in ("b200_static_plugin.cu", "b200_assign_static.cuh", "b200_assign_internal.cuh", "b200_common.cuh"):
+        with open(os.path.join(CSRC, dep), "rb") as fh:
+            h.update(fh.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    key = h.hexdigest()[:16]
+    jit_dir = os.path.join(CSRC, "_jit")
+    so = os.path.join(jit_dir, f"topo_{key}.so")
+    if not os.path.exists(so):
+        os.makedirs(jit_dir, exist_ok=True)
+        name = f"Topo_{key}"
+        header = os.path.join(jit_dir, f"topo_{key}.h")
+        with open(header, "w") as fh:
+            fh.write(codegen.emit(name, name.upper(), num_nodes, row, col, np.asarray(t0, dtype=np.float32),
+                                  [int(o) for o in origins], f"a {num_nodes}-node / {E}-link network"))
+        cmd = [_nvcc()] + NVCC_FLAGS + [f'-DB200_TOPO_HEADER="{header}"', f"-DB200_TOPO_NAME={name}", "-o", so + ".tmp",
+                                        os.path.join(CSRC, "b200_static_plugin.cu")]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise NativeLibraryError("nvcc failed on the specialised kernel:\n" + res.stderr[-4000:])
+        os.replace(so + ".tmp", so)
+        if verbose:
+            print(res.stderr)
+    check(lib().b200_register_static_plugin(so.encode()), "b200_register_static_plugin")
+    return so
 
 
 def check(rc: int, what: str) -> None:

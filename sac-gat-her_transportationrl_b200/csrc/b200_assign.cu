@@ -784,7 +784,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.od_q = prec == B200_F32 ? (const void *)g->od_q32 : (const void *)g->od_q64;
     p.small_blob = g->small_intq ? g->small_blob_i32 : (prec == B200_F32 ? g->small_blob32 : g->small_blob64);
     p.small_eid = g->small_eid; p.small_wpos = g->small_wpos;
-    p.st_t0 = g->st_t0; p.st_cap0 = g->st_cap0; p.st_eid = g->st_eid; p.st_wpos = g->st_wpos; p.st_origpos = g->st_origpos;
+    p.st_origpos = g->st_origpos;
     p.total_demand = g->total_demand;
     p.B = B; p.alpha = alpha; p.beta = beta;
     return p;

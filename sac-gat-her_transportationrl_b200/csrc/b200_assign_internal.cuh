@@ -89,10 +89,8 @@ struct Params {
     // small-network kernel only: TMA blob (node records + dense demand), per-slot link id / cost index
     const unsigned char *small_blob;
     const uint8_t *small_eid, *small_wpos;
-    // network-specialised kernel only: demand blob, per-slot t0 / cap0 / link id, origin positions
+    // network-specialised kernel only: TMA blob (dense demand + per-slot tables), origin positions
     const unsigned char *st_blob;
-    const float *st_t0, *st_cap0;
-    const uint8_t *st_eid, *st_wpos;
     const int32_t *st_origpos;
     double total_demand;
     // batch
@@ -154,6 +152,13 @@ __device__ REAL warp_pairwise(const REAL *a, int n)
 
 
 }  // namespace b200i
+
+// On-demand static-kernel plugins (b200_static_plugin.cu).  The ABI stamp changes whenever Params or
+// b200_graph change layout, so a stale cached plugin is rejected instead of misreading the structs.
+#define B200_PLUGIN_ABI (B200_VERSION * 1000 + (int)(sizeof(b200i::Params) % 997))
+typedef int (*b200_plugin_prepare_fn)(b200_graph *, const int32_t *, const int32_t *, const float *, const float *, int,
+                                      const int32_t *, const int32_t *, const double *, const int32_t *);
+typedef int (*b200_plugin_launch_fn)(const b200_graph *, const b200i::Params *, int, cudaStream_t);
 
 // launchers implemented in the other translation units
 int b200_launch_small(const b200_graph *g, const b200i::Params &p, int prec, cudaStream_t st);

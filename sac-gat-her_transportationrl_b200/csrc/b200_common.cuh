@@ -88,12 +88,11 @@ struct b200_graph {
     uint8_t *small_eid, *small_wpos;
     int small_ok, small_D, small_intq, force_general;
     // network-specialised kernel (b200_assign_static.cuh): set when the link list equals a compiled-in
-    // topology header; per-CSC-slot t0 / cap0 / link id in the header's slot order, internal origin
-    // positions, dense demand Q[internal node][32 lanes].  force_small = 1 (env B200_FORCE_SMALL)
+    // topology header; internal origin positions and the TMA blobs (dense demand Q[internal node][32
+    // lanes] followed by per-CSC-slot t0 / cap0 / link id / padded cost index tables).  force_small = 1 (env B200_FORCE_SMALL)
     // routes b200_assign through the generic lane-per-origin kernel instead (test hook)
     int static_ok, st_intq, force_small;
-    float *st_t0, *st_cap0;
-    uint8_t *st_eid, *st_wpos;
+    void *plugin_launch;   // launcher of the on-demand plugin that matched this topology (else built-in)
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32;
 };

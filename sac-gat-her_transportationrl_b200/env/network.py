@@ -15,7 +15,11 @@ from .. import _native
 
 
 class Network:
-    def __init__(self, graph_data, device_index: int = 0):
+    def __init__(self, graph_data, device_index: int = 0, specialize: bool = False):
+        """``specialize=True``: compile (once, cached) and use a straight-line assignment kernel
+        generated for THIS topology, as Sioux Falls gets out of the box (small networks only,
+        ``_native.specialize``)."""
+        self.specialize = bool(specialize)
         g = graph_data
         self.graph_data = g
         self.num_nodes = int(g.num_nodes)
@@ -42,6 +46,8 @@ class Network:
     def handle(self):
         if self._handle is None:
             lib = _native.lib()
+            if self.specialize:
+                _native.specialize(self.num_nodes, self.edge_index[0], self.edge_index[1], self.t0, self.origins)
             row = np.ascontiguousarray(self.edge_index[0], dtype=np.int32)
             col = np.ascontiguousarray(self.edge_index[1], dtype=np.int32)
             out = C.c_void_p()

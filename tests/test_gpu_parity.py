@@ -419,6 +419,37 @@ def test_general_small_and_static_kernels_agree(b200env, native_lib, sf_graph, s
         np.testing.assert_allclose(c["tstt"], b["tstt"], rtol=rtol)
 
 
+def test_on_demand_specialised_kernel_for_another_small_network(b200env, native_lib, monkeypatch):
+    """``Network(specialize=True)`` compiles the straight-line kernel template for the network at
+    hand (cached plugin) - results must equal the generic lane-per-origin kernel and the oracle."""
+    from oracle.c_oracle import COracle
+    g = b200env.synthetic.small_grid(4, 5, 6, seed=3)
+    orc = COracle.from_graph_data(g)
+    E = len(g.edges)
+    rng = np.random.default_rng(2)
+    masks = np.zeros((40, E), np.uint8)
+    for b in range(40):
+        masks[b, rng.choice(E, max(1, int(E * 0.2)), replace=False)] = 1
+    monkeypatch.setenv("B200_FORCE_SMALL", "1")
+    generic = b200env.AssignmentEngine(b200env.Network(g), _dev(), "fp32")
+    monkeypatch.delenv("B200_FORCE_SMALL")
+    assert generic.kernel_name == "assign_small_kernel"
+    special = b200env.AssignmentEngine(b200env.Network(g, specialize=True), _dev(), "fp32")
+    special64 = b200env.AssignmentEngine(b200env.Network(g, specialize=True), _dev(), "fp64")
+    assert special.kernel_name == "assign_static_kernel"
+    for method in ("msa", "fw"):
+        a, b = _assign(generic, masks, 20, method), _assign(special, masks, 20, method)
+        assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["tstt"], b["tstt"])
+        assert np.array_equal(a["unassigned"], b["unassigned"]) and np.array_equal(a["status"], b["status"])
+        for s_ in (0, 17, 39):
+            o = orc.assign(masks[s_], None, 20, method)
+            assert np.array_equal(b["flow"][s_], o["flow"]) and b["tstt"][s_] == o["tstt"]
+        o64 = orc.assign(masks[5], None, 20, method, dtype=np.float64)
+        assert np.array_equal(_assign(special64, masks[5:6], 20, method)["flow"][0], o64["flow"])
+    # Sioux Falls is untouched by the plugin (different link list)
+    assert _engine(b200env, b200env.load_sioux_falls(), "fp32").kernel_name == "assign_static_kernel"
+
+
 def test_fractional_demand_uses_float_scatter_add(b200env, native_lib, sf_graph):
     """Non-integer demands take the float scatter-add path of the small-network kernel (integer
     demands take the exact int32 redux path); sums are then order-dependent -> tolerance parity."""

@@ -100,3 +100,29 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
                 assert "liboracle" not in text and "ref_port" not in text, f
+
+
+def test_topology_codegen_is_deterministic_and_consistent(b200env, sf_graph):
+    """The generated topology header is data only; its CSC must describe exactly the uploaded link
+    list, in-links by ascending original tail id, nodes renumbered by sweep position."""
+    import importlib
+    import re
+    cg = importlib.import_module("sac-gat-her_transportationrl_b200.codegen")
+    net = b200env.Network(sf_graph)
+    row, col = net.edge_index
+    text = cg.emit("TopoX", "X", net.num_nodes, row, col, net.t0, [int(o) for o in net.origins], "test")
+    assert text == cg.emit("TopoX", "X", net.num_nodes, row, col, net.t0, [int(o) for o in net.origins], "test")
+    arr = {m.group(1): [int(x) for x in m.group(2).split(",")]
+           for m in re.finditer(r"constexpr int (\w+)\[\d+\] = \{([^}]*)\}", text)}
+    node, koff, src, eid = arr["NODE"], arr["KOFF"], arr["SRC"], arr["EID"]
+    assert sorted(node) == list(range(24)) and sorted(eid) == list(range(76)) and koff[-1] == 76
+    for i in range(24):
+        links = list(range(koff[i], koff[i + 1]))
+        assert all(col[eid[k]] == node[i] for k in links)           # slot k enters internal node i
+        assert all(node[src[k]] == row[eid[k]] for k in links)      # from the right tail
+        tails = [int(row[eid[k]]) for k in links]
+        assert tails == sorted(tails)                                # ascending ORIGINAL tail id (tie rule)
+    # the committed built-in header is what the generator produces today
+    committed = open(os.path.join(os.path.dirname(__file__), "..", "sac-gat-her_transportationrl_b200", "csrc",
+                                  "b200_topo_siouxfalls.h")).read()
+    assert arr["SRC"] == [int(x) for x in re.search(r"SRC\[76\] = \{([^}]*)\}", committed).group(1).split(",")]

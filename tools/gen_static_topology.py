@@ -22,98 +22,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
 
 
-def _sweeps(order, inl, row, w, origins, cap=400):
-    N = len(order)
-    d = np.full((len(origins), N), np.inf)
-    for i, o in enumerate(origins):
-        d[i, o] = 0.0
-    s = 0
-    while True:
-        changed = False
-        for v in (order if s % 2 == 0 else order[::-1]):
-            for e in inl[v]:
-                c = d[:, row[e]] + w[e]
-                m = c < d[:, v]
-                if m.any():
-                    d[m, v] = c[m]
-                    changed = True
-        s += 1
-        if not changed or s > cap:
-            return s
+from importlib import import_module
 
-
-def choose_order(N, row, col, t0, origins):
-    E = len(row)
-    inl = [[] for _ in range(N)]
-    for e in range(E):
-        inl[col[e]].append(e)
-    rng = np.random.default_rng(12345)
-    patterns = [t0.astype(np.float64)]
-    for _ in range(5):
-        w = t0.astype(np.float64) * (1.0 + 0.5 * rng.random(E))
-        w[rng.random(E) < 0.3] = 1e6
-        patterns.append(w)
-    best = None
-    for root in range(N):
-        dist = np.full(N, np.inf)
-        dist[root] = 0.0
-        done = np.zeros(N, bool)
-        for _ in range(N):
-            cand = np.where(done, np.inf, dist)
-            u = int(np.argmin(cand))
-            if not np.isfinite(cand[u]):
-                break
-            done[u] = True
-            for e in range(E):  # undirected free-flow distances
-                a, b = int(row[e]), int(col[e])
-                if a == u and dist[u] + t0[e] < dist[b]:
-                    dist[b] = dist[u] + t0[e]
-                if b == u and dist[u] + t0[e] < dist[a]:
-                    dist[a] = dist[u] + t0[e]
-        order = [int(x) for x in np.argsort(dist, kind="stable")]
-        cost = sum(_sweeps(order, inl, row, w, origins) for w in patterns)
-        if best is None or cost < best[0]:
-            best = (cost, order, root)
-    return best[1], best[2], best[0]
-
-
-def emit(name: str, guard: str, N, row, col, t0, origins, source: str) -> str:
-    order, root, cost = choose_order(N, row, col, t0, origins)
-    pos = np.empty(N, np.int64)
-    pos[order] = np.arange(N)
-    E = len(row)
-    koff, src, eid = [0], [], []
-    for i in range(N):
-        v = order[i]
-        links = sorted((int(row[e]), e) for e in range(E) if col[e] == v)  # ascending ORIGINAL tail id
-        for u, e in links:
-            src.append(int(pos[u]))
-            eid.append(e)
-        koff.append(len(src))
-    maxd = max(koff[i + 1] - koff[i] for i in range(N))
-
-    def arr(xs):
-        return "{" + ", ".join(str(int(x)) for x in xs) + "}"
-
-    return f"""// GENERATED by tools/gen_static_topology.py from {source} - data only, do not edit.
-// Topology of one network for the network-specialised kernel (b200_assign_static.cuh).
-// Internal node index = position in the Gauss-Seidel sweep order (ascending free-flow distance
-// from original node {root}; {cost} sweeps over the 6 calibration patterns).
-#pragma once
-struct {name} {{
-    static constexpr int N = {N}, E = {E}, MAXD = {maxd};
-    // original 0-based node id of internal node i
-    static constexpr int NODE[{N}] = {arr(order)};
-    // CSC over internal nodes: in-links of node i are slots KOFF[i] .. KOFF[i+1]-1, listed by
-    // ascending ORIGINAL tail id; SRC = internal tail index, EID = link id (TNTP row order)
-    static constexpr int KOFF[{N + 1}] = {arr(koff)};
-    static constexpr int SRC[{E}] = {arr(src)};
-    static constexpr int EID[{E}] = {arr(eid)};
-    // the link list this header was generated from (row -> col, 0-based), matched at graph upload
-    static constexpr int ROW[{E}] = {arr(row)};
-    static constexpr int COL[{E}] = {arr(col)};
-}};
-"""
+emit = import_module("sac-gat-her_transportationrl_b200.codegen").emit
 
 
 def main() -> None:
