@@ -22,7 +22,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 import shutil
 import subprocess
-from typing import List
+
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")

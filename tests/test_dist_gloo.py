@@ -3,7 +3,6 @@ all-gather order, gradient averaging."""
 import os
 import sys
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

@@ -16,7 +16,6 @@ from __future__ import annotations
 import os
 import sys
 
-import numpy as np
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)

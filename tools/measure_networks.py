@@ -3,7 +3,6 @@ numbers quoted in DESIGN.md).  python tools/measure_networks.py [sf an cs]"""
 import json
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
