@@ -159,9 +159,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp
 // Queue tails live in a group-uniform register: new entries are placed by ballot + popcount, the
 // only shared-memory atomics are the "already queued" bits.  Link loops are unrolled by kLinkUnroll
 // so the dependent shared-memory loads of one step are issued together.
-constexpr int kLinkUnroll = 4;
-
-template <typename REAL, int G>
+template <typename REAL, int G, int kLinkUnroll = 4>
 __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, const uint16_t *tree = nullptr)
 {
     const int lane = threadIdx.x & 31, gl = lane & (G - 1), N = c.N;
@@ -688,7 +686,7 @@ __device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double
 // MINB = 2: at most 64 registers per thread, for networks small enough that several CTAs share an
 // SM (occupancy is what this latency-bound kernel lives on); MINB = 1: up to 128 registers when
 // shared memory allows only one CTA per SM anyway (Chicago-Sketch-size)
-template <typename REAL, int MINB, int G>
+template <typename REAL, int MINB, int G, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -725,7 +723,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
                 const int o = s < p.O ? __ldg(p.origins + s) : -1;
                 const WarpScratch ws = warp_scratch(c, warp, group, OPW);
                 uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + (s < p.O ? s : 0)) * p.N;
-                capped |= warp_sssp<REAL, G>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
+                capped |= warp_sssp<REAL, G, U>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
                 if (o >= 0 && p.warm)
                     for (int v = gl; v < p.N; v += G) tree[v] = ws.pk[v];   // next iteration's warm start
                 un += warp_aon<REAL, G>(c, p, s, o, ws);
@@ -982,10 +980,12 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
         const bool one_cta = 2 * (smem + 1024) > 228 * 1024;   // shared memory admits a single CTA per SM
         cudaStream_t st = (cudaStream_t)stream;
         p.slots = 32 / g->group_lanes;
-#define B200_LAUNCH_FUSED(REAL, G)                                                              \
-    (one_cta ? launch_cta_kernel(assign_fused_kernel<REAL, 1, G>, g, prec, p, st, true)          \
-             : launch_cta_kernel(assign_fused_kernel<REAL, 2, G>, g, prec, p, st, true))
-        rc = prec == B200_F32 ? B200_LAUNCH_FUSED(float, 32) : B200_LAUNCH_FUSED(double, 32);   // see group_lanes
+#define B200_LAUNCH_FUSED(REAL, G, U)                                                           \
+    (one_cta ? launch_cta_kernel(assign_fused_kernel<REAL, 1, G, U>, g, prec, p, st, true)       \
+             : launch_cta_kernel(assign_fused_kernel<REAL, 2, G, U>, g, prec, p, st, true))
+        // G: see group_lanes.  U = 2 was measured on the Anaheim-size network (2.2 links/node): 6 % slower
+        // than 4 (more loop trips and votes), so the link loops stay 4-wide everywhere.
+        rc = prec == B200_F32 ? B200_LAUNCH_FUSED(float, 32, 4) : B200_LAUNCH_FUSED(double, 32, 4);
 #undef B200_LAUNCH_FUSED
     }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;
