@@ -514,18 +514,51 @@ __device__ void cta_tstt(Cta<REAL> &c, const Params &p, REAL *scratch, double un
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-template <typename REAL>
-__global__ void bpr_kernel(Params p)
+// S1 is the one stage that really streams from HBM (9 bytes per link: flow + mask in, cost out).
+// Grid-stride sweep, VEC links per thread per step (VEC = 4: 16-byte flow loads / cost stores and
+// 4-byte mask loads when rows are 16-byte multiples), link index within the row kept by an
+// incremental wrap instead of a 64-bit modulo per element; t0 / cap0 come from L1 (__ldg).
+template <typename REAL, int VEC>
+__global__ void __launch_bounds__(256) bpr_kernel(Params p)
 {
-    const REAL *flow = (const REAL *)p.flow;
-    REAL *t = (REAL *)p.t;
-    const long long total = (long long)p.B * p.E;
+    const long long total = (long long)p.B * p.E / VEC;           // vectors
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int E = p.E;
+    int e = (int)((i * VEC) % E);
+    const int step = (int)((stride * VEC) % E);
     const bool beta4 = p.beta == 4.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int e = (int)(i % p.E);
-        t[i] = p.dmg[i] ? (REAL)1e6
-                        : Bpr<REAL>::eval(flow[i], (REAL)__ldg(p.cap0 + e), (REAL)__ldg(p.t0 + e), (REAL)p.alpha,
-                                          (REAL)p.beta, beta4);
+    const REAL alpha = (REAL)p.alpha, beta = (REAL)p.beta;
+    if constexpr (VEC == 4 && sizeof(REAL) == 4) {
+        auto eval4 = [&](const float4 &f, const uchar4 &d, int ee) {
+            const float4 c = __ldg((const float4 *)(p.cap0 + ee)), z = __ldg((const float4 *)(p.t0 + ee));
+            float4 t;
+            t.x = d.x ? 1e6f : Bpr<float>::eval(f.x, c.x, z.x, alpha, beta, beta4);
+            t.y = d.y ? 1e6f : Bpr<float>::eval(f.y, c.y, z.y, alpha, beta, beta4);
+            t.z = d.z ? 1e6f : Bpr<float>::eval(f.z, c.z, z.z, alpha, beta, beta4);
+            t.w = d.w ? 1e6f : Bpr<float>::eval(f.w, c.w, z.w, alpha, beta, beta4);
+            return t;
+        };
+        // two vectors per trip: both loads are in flight before the first result is needed
+        for (; i + stride < total; i += 2 * stride) {
+            const float4 f0 = ((const float4 *)p.flow)[i], f1 = ((const float4 *)p.flow)[i + stride];
+            const uchar4 d0 = ((const uchar4 *)p.dmg)[i], d1 = ((const uchar4 *)p.dmg)[i + stride];
+            int e1 = e + step;
+            if (e1 >= E) e1 -= E;
+            ((float4 *)p.t)[i] = eval4(f0, d0, e);
+            ((float4 *)p.t)[i + stride] = eval4(f1, d1, e1);
+            e = e1 + step;
+            if (e >= E) e -= E;
+        }
+        if (i < total) ((float4 *)p.t)[i] = eval4(((const float4 *)p.flow)[i], ((const uchar4 *)p.dmg)[i], e);
+    } else {
+        for (; i < total; i += stride) {
+            ((REAL *)p.t)[i] = p.dmg[i] ? (REAL)1e6
+                                        : Bpr<REAL>::eval(((const REAL *)p.flow)[i], (REAL)__ldg(p.cap0 + e),
+                                                          (REAL)__ldg(p.t0 + e), alpha, beta, beta4);
+            e += step;
+            if (e >= E) e -= E;
+        }
     }
 }
 
@@ -903,9 +936,15 @@ extern "C" int b200_bpr(const b200_graph *g, int B, int prec, const void *flow, 
     p.flow = (void *)flow; p.dmg = dmg; p.t = t;
     const long long total = (long long)B * g->E;
     const int threads = 256;
-    const int grid = (int)std::min<long long>((total + threads - 1) / threads, (long long)g->num_sms * 8);
-    if (prec == B200_F32) bpr_kernel<float><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
-    else bpr_kernel<double><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    // vector path: rows are multiples of 16 bytes and every base pointer is 16-byte aligned
+    const bool vec = prec == B200_F32 && g->E % 4 == 0 &&
+                     (((uintptr_t)flow | (uintptr_t)t | (uintptr_t)g->cap0 | (uintptr_t)g->t0) % 16 == 0) &&
+                     (uintptr_t)dmg % 4 == 0;
+    const long long units = vec ? total / 4 : total;
+    const int grid = (int)std::min<long long>((units + threads - 1) / threads, (long long)g->num_sms * 8);
+    if (vec) bpr_kernel<float, 4><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    else if (prec == B200_F32) bpr_kernel<float, 1><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
+    else bpr_kernel<double, 1><<<grid, threads, 0, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());
     return 0;
 }
