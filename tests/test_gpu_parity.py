@@ -319,6 +319,38 @@ def test_properties_conservation_determinism_sharding(b200env, native_lib, sf_gr
     assert np.all(np.isfinite(a["gap"])) and np.all(a["gap"] > -1e-9)
 
 
+@pytest.mark.parametrize("which,B,K,method", [("an", 1024, 20, "fw"), ("cs", 64, 6, "msa")])
+def test_properties_large_networks_full_batches(b200env, native_lib, which, B, K, method):
+    """BASELINE.json configs 3 / 4 at (or near) their named batch sizes: the general kernel (frontier
+    shortest paths, warm-started trees, Kahn peel, cluster mode for the small shards) must be
+    deterministic, invariant to how the batch is sharded over launches / GPUs - including the shard
+    sizes of an 8-GPU run, which take the thread-block-cluster path - and must conserve flow."""
+    g = b200env.synthetic.anaheim_size(0) if which == "an" else b200env.synthetic.chicago_sketch_size(0)
+    eng = _engine(b200env, g, "fp32")
+    E = eng.E
+    rng = np.random.default_rng(99)
+    masks = np.zeros((B, E), np.uint8)
+    for b in range(B):
+        masks[b, rng.choice(E, int(E * 0.3), replace=False)] = 1
+    a = _assign(eng, masks, K, method)
+    assert np.array_equal(a["flow"], _assign(eng, masks, K, method)["flow"])            # run to run
+    shard = _assign(eng, masks[: B // 8], K, method)                                     # one rank of an 8-GPU run
+    assert np.array_equal(shard["flow"], a["flow"][: B // 8]) and np.array_equal(shard["tstt"], a["tstt"][: B // 8])
+    assert np.all(a["status"] == 0) and np.all(a["unassigned"] == 0) and np.all(np.isfinite(a["gap"]))
+    row, col = eng.net.edge_index
+    N = eng.N
+    prod, attr = np.zeros(N), np.zeros(N)
+    for (o, d), q in g.od_demand.items():
+        prod[o - 1] += q
+        attr[d - 1] += q
+    f = a["flow"][:32].astype(np.float64)
+    net_out = np.zeros((32, N))
+    np.add.at(net_out.T, row, f.T)
+    np.add.at(net_out.T, col, -f.T)
+    scale = max(prod.max(), 1.0)
+    np.testing.assert_allclose(net_out / scale, np.broadcast_to((prod - attr) / scale, net_out.shape), atol=2e-5)
+
+
 def test_aon_total_equals_demand_times_path_length(b200env, native_lib, sf_graph, sf_oracle, golden):
     """sum_e aux_e == sum_od q * hops(o,d) on the trees the kernel itself produced."""
     eng = _engine(b200env, sf_graph, "fp64")
