@@ -270,6 +270,10 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
     }
 }
 
+// one warp per (node, head) pair of a graph, at most 32 warps: a CTA never carries idle warps, and
+// small slabs (one head) leave room for a second CTA on the SM
+int gat_threads(int N, int H) { return 32 * std::min(32, std::max(1, N * H)); }
+
 int check_common(const b200_graph *g, int B, int H, int C)
 {
     B200_REQUIRE(g && B >= 0 && H > 0 && C > 0, "bad argument");
@@ -304,16 +308,17 @@ extern "C" int b200_gat_edge_softmax_aggregate_fwd(const b200_graph *g, int B, i
     const size_t smem = 128 + 2 * gat_stage_bytes(g->N, g->E, H, C);
     cudaStream_t st = (cudaStream_t)stream;
     const bool narrow = g->max_in_deg + 1 <= 8;
+    const int threads = gat_threads(g->N, H);
     if (smem <= 226 * 1024) {
         auto kern = narrow ? gat_fwd_kernel<true, 8> : gat_fwd_kernel<true, 32>;
         B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatThreads, smem));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
         const int grid = std::min(B, std::max(per_sm, 1) * g->num_sms);
-        kern<<<grid, kGatThreads, smem, st>>>(p);
+        kern<<<grid, threads, smem, st>>>(p);
     } else {
         auto kern = narrow ? gat_fwd_kernel<false, 8> : gat_fwd_kernel<false, 32>;
-        kern<<<std::min(B, g->num_sms * 2), kGatThreads, 128, st>>>(p);
+        kern<<<std::min(B, g->num_sms * 2), threads, 128, st>>>(p);
     }
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -340,12 +345,14 @@ extern "C" int b200_gat_edge_softmax_aggregate_bwd(const b200_graph *g, int B, i
     const size_t smem_staged = 128 + graw_bytes + 2 * slab_bytes;
     if (smem_staged <= 220 * 1024) {
         B200_CUDA(cudaFuncSetAttribute(gat_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
-        gat_bwd_kernel<true><<<std::min(B, g->num_sms), kGatThreads, smem_staged, st>>>(p);
+        int per_sm = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gat_bwd_kernel<true>, gat_threads(g->N, H), smem_staged));
+        gat_bwd_kernel<true><<<std::min(B, std::max(per_sm, 1) * g->num_sms), gat_threads(g->N, H), smem_staged, st>>>(p);
     } else {
         const size_t smem = 128 + graw_bytes;
         B200_REQUIRE(smem <= 220 * 1024, "network too large for the GAT backward kernel");
         B200_CUDA(cudaFuncSetAttribute(gat_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gat_bwd_kernel<false><<<std::min(B, g->num_sms * 4), kGatThreads, smem, st>>>(p);
+        gat_bwd_kernel<false><<<std::min(B, g->num_sms * 2), gat_threads(g->N, H), smem, st>>>(p);
     }
     B200_CUDA(cudaGetLastError());
     return 0;
