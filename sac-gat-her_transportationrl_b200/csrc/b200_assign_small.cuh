@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32, B200_SMALL_MINB) assign_smal
         for (int v = 0; v < N; ++v) {
             const int u = pu[v * O];
             if (u != 255) cnt[u * O] += 1;
-            else if (v != orig) un += (double)Qc[v * O];   // unreachable destination
+            else un += (double)Qc[v * O];   // unreachable destination, or demand to the origin itself (reference :496)
         }
         int top = 0;
         for (int v = 0; v < N; ++v)

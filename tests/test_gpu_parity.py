@@ -389,6 +389,37 @@ def test_unreachable_demand_is_penalised(b200env, native_lib):
     assert np.array_equal(out["flow"][0], o["flow"])
 
 
+def test_demand_to_the_origin_itself_is_unassigned_in_every_kernel(b200env, native_lib, sf_graph, monkeypatch):
+    """`if d == o or prow[d] < 0: unassigned += q` (reference :496): an OD pair (o, o) never enters
+    the network; all three fused kernels and the oracle must agree on it."""
+    from oracle.c_oracle import COracle
+    od = dict(sf_graph.od_demand)
+    od[(3, 3)] = 700.0
+    od[(10, 10)] = 50.0
+    g = b200env.GraphData(num_nodes=24, edges=sf_graph.edges, od_demand=od)
+    orc = COracle.from_graph_data(g)
+    rng = np.random.default_rng(4)
+    masks = np.zeros((6, 76), np.uint8)
+    for b in range(6):
+        masks[b, rng.choice(76, 22, replace=False)] = 1
+    engines = {"static": _engine(b200env, g, "fp32")}
+    monkeypatch.setenv("B200_FORCE_SMALL", "1")
+    engines["small"] = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_FORCE_SMALL")
+    monkeypatch.setenv("B200_FORCE_GENERAL", "1")
+    engines["general"] = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_FORCE_GENERAL")
+    assert [e.kernel_name for e in engines.values()] == ["assign_static_kernel", "assign_small_kernel", "assign_fused_kernel"]
+    for name, eng in engines.items():
+        out = _assign(eng, masks, 10, "msa")
+        assert np.all(out["unassigned"] == 750.0), name
+        assert np.all(out["status"] == 2), name                      # B200_ST_UNASSIGNED
+        for b in (0, 5):
+            o = orc.assign(masks[b], None, 10, "msa")
+            assert o["unassigned"] == 750.0
+            assert np.array_equal(out["flow"][b], o["flow"]) and out["tstt"][b] == o["tstt"], name
+
+
 def test_empty_batch_and_bad_arguments(b200env, native_lib, sf_graph):
     eng = _engine(b200env, sf_graph, "fp32")
     d = _dev()
