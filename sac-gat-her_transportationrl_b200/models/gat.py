@@ -101,8 +101,13 @@ class GATConvB200(nn.Module):
         B, N, _ = x.shape
         H, C = self.heads, self.out_channels
         xw = self.lin(x).view(B, N, H, C)
-        a_src = (xw * self.att_src).sum(-1)
-        a_dst = (xw * self.att_dst).sum(-1)
+        # <lin(x), att_src> and <lin(x), att_dst> per head as ONE small GEMM on x: the attention vectors
+        # are folded into the projection ([2H, in] matrix) instead of re-reading the [B, N, H*C]
+        # projected features twice (same parameters, same sums up to association)
+        w3 = self.lin.weight.view(H, C, -1)
+        w_att = torch.cat([(w3 * self.att_src.view(H, C, 1)).sum(dim=1), (w3 * self.att_dst.view(H, C, 1)).sum(dim=1)])
+        a_both = F.linear(x, w_att)
+        a_src, a_dst = a_both[..., :H], a_both[..., H:]
         E = self.network.num_edges
         if self.lin_edge is not None and edge_attr is not None:
             # self-loop attributes = mean of the attributes of the node's incoming links (fill_value='mean')
@@ -110,8 +115,11 @@ class GATConvB200(nn.Module):
             loop_attr.index_add_(1, self._dst, edge_attr)
             loop_attr = loop_attr / self._in_deg.view(1, N, 1)
             full = torch.cat([edge_attr, loop_attr], dim=1)
-            ew = self.lin_edge(full).view(B, E + N, H, C)
-            a_edge = (ew * self.att_edge).sum(-1)
+            # <lin_edge(e), att_edge> per head without the [B, E+N, H*C] projection PyG materialises:
+            # the projected link features are used for nothing else, so the two linear maps fold
+            # into one [H, edge_dim] matrix (same parameters, same sum up to association)
+            w_eff = (self.lin_edge.weight.view(H, C, -1) * self.att_edge.view(H, C, 1)).sum(dim=1)
+            a_edge = F.linear(full, w_eff)
         else:
             a_edge = torch.zeros(B, E + N, H, device=x.device, dtype=xw.dtype)
         return xw, a_src, a_dst, a_edge

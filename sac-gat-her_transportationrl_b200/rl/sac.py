@@ -55,10 +55,16 @@ class _EdgeHead(nn.Module):
         node_x = self.node_norm(node_x)
         edge_attr = self.edge_norm(edge_attr)
         node_emb, ctx, attn = self.encoder(node_x, edge_attr, return_attention=return_attention)
-        B, E = edge_attr.shape[0], edge_attr.shape[1]
-        edge_emb = torch.cat([node_emb[:, self._src], node_emb[:, self._dst], edge_attr,
-                              ctx.unsqueeze(1).expand(B, E, ctx.shape[-1])], dim=2)
-        return self.edge_mlp(edge_emb).squeeze(-1), attn
+        # First linear of edge_mlp on [emb(src) | emb(dst) | edge_attr | ctx] WITHOUT materialising the
+        # [B, E, 4*embed + edge_in] concatenation the reference builds (src/rl/sac.py:43, :75): the
+        # weight is split by column block, the node blocks are applied per NODE (N rows instead of E)
+        # and gathered afterwards, the context block once per graph.  Same parameters, same sum.
+        lin0 = self.edge_mlp[0]
+        D = node_emb.shape[-1]
+        w_src, w_dst, w_edge, w_ctx = torch.split(lin0.weight, [D, D, edge_attr.shape[-1], ctx.shape[-1]], dim=1)
+        h = (F.linear(node_emb, w_src)[:, self._src] + F.linear(node_emb, w_dst)[:, self._dst]
+             + F.linear(edge_attr, w_edge) + F.linear(ctx, w_ctx, lin0.bias).unsqueeze(1))
+        return self.edge_mlp[2](self.edge_mlp[1](h)).squeeze(-1), attn
 
 
 class Actor(_EdgeHead):
