@@ -87,6 +87,30 @@ def select_greedy_one_step(env: BatchedRepairEnv, state: Optional[BatchedEnvStat
     return best
 
 
+def make_actor_policy(agent, deterministic: bool = True, generator: Optional[torch.Generator] = None) -> Policy:
+    """The trained policy as a batched ``Policy`` (reference src/eval.py:40-48 wraps
+    ``agent.select_action`` the same way for one state): argmax of the masked link probabilities,
+    or a sample from them."""
+    def policy(state: BatchedEnvState) -> torch.Tensor:
+        out = agent.select_action(state.node_features, state.edge_features, state.action_mask,
+                                  deterministic=deterministic, generator=generator)
+        return out.action.to(torch.int32)
+    return policy
+
+
+def evaluate(env: BatchedRepairEnv, policies: Dict[str, Policy], reward_scale: float = 1.0, max_steps: int = 0,
+             damage_masks=None) -> Dict[str, Dict[str, float]]:
+    """Every policy on the SAME damage scenarios (reference src/eval.py:51-86 loops over seeds and
+    policies one episode at a time): mean over scenarios of the reference's episode metrics."""
+    if damage_masks is None:
+        damage_masks = env.sample_damage_masks(env.damaged_ratio)
+    table = {}
+    for name, pol in policies.items():
+        res = run_episode(env, pol, reward_scale=reward_scale, max_steps=max_steps, damage_masks=damage_masks)
+        table[name] = {k: float(res[k].double().mean()) for k in ("reward", "tstt_last", "tstt_mean", "tstt_auc", "steps")}
+    return table
+
+
 def get_baseline_policies(env: BatchedRepairEnv, node_betweenness: Optional[torch.Tensor] = None) -> Dict[str, Policy]:
     """Same names as the reference's ``get_baseline_policies`` (:104-113)."""
     pol: Dict[str, Policy] = {

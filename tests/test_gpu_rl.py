@@ -115,3 +115,21 @@ def test_batched_trainer_runs_episodes_updates_and_resets(b200env, native_lib, s
     assert int(tr.ep_steps.max()) <= 6
     # a reset scenario is a fresh episode: damage restored to 7 links, flows re-assigned
     assert torch.all(tr.env.is_damaged.sum(dim=1) <= 7) and torch.all(tr.env.tstt > 0)
+
+
+def test_evaluate_policies_on_common_scenarios(b200env, native_lib, sf_graph):
+    """eval.py-style comparison: trained-policy wrapper, greedy and a simple heuristic on the same
+    damage draws; greedy must not end worse than 'first damaged link' on average."""
+    rl = _rl()
+    bl = importlib.import_module("sac-gat-her_transportationrl_b200.baselines")
+    B = 12
+    env = b200env.BatchedRepairEnv(sf_graph, B, assignment_method="msa", assignment_iters=8, device="cuda:0",
+                                   seeds=list(range(B)), damaged_ratio=0.08)
+    agent = rl.DiscreteSAC(env.network, 4, 6, 32, 16, device="cuda:0")
+    pols = {"actor": bl.make_actor_policy(agent), "greedy": lambda s: bl.select_greedy_one_step(env),
+            "first": lambda s: torch.argmax(s.action_mask, dim=1).to(torch.int32)}
+    table = bl.evaluate(env, pols, max_steps=20)
+    assert set(table) == {"actor", "greedy", "first"}
+    k = max(1, int(76 * 0.08))
+    assert all(t["steps"] == k for t in table.values())            # masked policies always repair a damaged link
+    assert table["greedy"]["tstt_auc"] <= table["first"]["tstt_auc"] * (1 + 1e-9)
