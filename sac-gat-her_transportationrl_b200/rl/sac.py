@@ -203,8 +203,8 @@ class DiscreteSAC:
 
     @torch.no_grad()
     def _soft_update(self, src: nn.Module, tgt: nn.Module) -> None:
-        for p, tp in zip(src.parameters(), tgt.parameters()):
-            tp.lerp_(p, self.target_tau)
+        # tp <- (1 - tau) tp + tau p (reference :289-291), one fused multi-tensor launch
+        torch._foreach_lerp_(list(tgt.parameters()), list(src.parameters()), self.target_tau)
 
     # ---- checkpoints in the reference's layout (:265-287) ---------------------------------------
     def save(self, path: str) -> None:
