@@ -41,7 +41,7 @@ def default_config() -> Dict:
                 unassigned_penalty=1e4, max_steps=100, her_ratio=0.0, gat_layers=3, hidden_dim=256, embed_dim=256,
                 lr=1e-4, actor_lr=3e-5, critic_lr=1e-4, alpha_lr=1e-4, gamma=0.99, target_tau=0.001, grad_clip=1.0,
                 share_critic_encoder=False, seed=42, alpha_max=2.5, alpha_init=0.1, target_entropy_ratio=0.2,
-                precision="fp32")
+                precision="fp32", allow_tf32=False)
 
 
 class BatchedTrainer:
@@ -49,6 +49,10 @@ class BatchedTrainer:
         self.cfg = default_config()
         self.cfg.update(cfg or {})
         c = self.cfg
+        if c["allow_tf32"]:
+            # opt-in: the dense projections run on the tensor cores in TF32 (actor forward 3.5 -> 2.3 ms
+            # per 1024 envs); the default keeps the reference's fp32 GEMMs
+            torch.backends.cuda.matmul.allow_tf32 = True
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.device = torch.device(device)
