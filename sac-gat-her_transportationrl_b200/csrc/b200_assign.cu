@@ -159,6 +159,15 @@ __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp
 // Queue tails live in a group-uniform register: new entries are placed by ballot + popcount, the
 // only shared-memory atomics are the "already queued" bits.  Link loops are unrolled by kLinkUnroll
 // so the dependent shared-memory loads of one step are issued together.
+// `cond` is uniform within a group of G lanes; true if it holds in any group of the warp (with one
+// group per warp that is just `cond`: no vote needed)
+template <int G>
+__device__ __forceinline__ bool group_any(bool cond)
+{
+    if constexpr (G == 32) return cond;
+    else return __any_sync(0xffffffffu, cond);
+}
+
 template <typename REAL, int G, int kLinkUnroll = 4>
 __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, const uint16_t *tree = nullptr)
 {
@@ -182,9 +191,9 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
             count = 1;
         }
         __syncwarp();
-        while (__any_sync(FULL, count > 0)) {   // breadth-first over the old tree's children
+        while (group_any<G>(count > 0)) {   // breadth-first over the old tree's children
             int ntail = 0;
-            for (int base = 0; __any_sync(FULL, base < count); base += G) {
+            for (int base = 0; group_any<G>(base < count); base += G) {
                 const bool valid = base + gl < count;
                 const int u = valid ? (int)cur[base + gl] : 0;
                 const double du = valid ? dist[u] : 0.0;
@@ -234,9 +243,9 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
     }
     __syncwarp();
     int rounds = 0, capped = 0;
-    while (__any_sync(FULL, count > 0)) {
+    while (group_any<G>(count > 0)) {
         int ntail = 0;
-        for (int base = 0; __any_sync(FULL, base < count); base += G) {
+        for (int base = 0; group_any<G>(base < count); base += G) {
             const bool valid = base + gl < count;
             const int v = valid ? (int)cur[base + gl] : 0;
             if (valid) atomicAnd(&s.mask[v >> 5], ~(1u << (v & 31)));
@@ -369,9 +378,9 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
         count += __popc(m);
     }
     __syncwarp();
-    while (__any_sync(FULL, count > 0)) {
+    while (group_any<G>(count > 0)) {
         int ntail = 0;
-        for (int base = 0; __any_sync(FULL, base < count); base += G) {
+        for (int base = 0; group_any<G>(base < count); base += G) {
             bool ready = false;
             int u = 0;
             if (base + gl < count) {
