@@ -179,7 +179,7 @@ class BatchedRepairEnv:
                  reward_beta: float = 10.0, reward_gamma: float = 0.1, reward_clip: float = 0.0,
                  capacity_damage: float = 1e-3, unassigned_penalty: float = 2e7, fixed_damage: bool = False,
                  fixed_damage_seed: Optional[int] = None, seed: int = 0, seeds: Optional[Sequence[int]] = None,
-                 line_search_iters: int = 24):
+                 line_search_iters: int = 24, specialize_kernel: bool = False):
         if assignment_iters <= 0:
             raise ValueError("assignment_iters must be > 0 to update TSTT.")
         self.assignment_method = assignment_method.lower()
@@ -190,7 +190,8 @@ class BatchedRepairEnv:
             raise ValueError(f"unknown assignment_method {assignment_method!r}")
         if reward_mode not in REWARD_MODES:
             reward_mode = "delta"  # the reference's else-branch (:285-286)
-        self.network = graph_data if isinstance(graph_data, Network) else Network(graph_data)
+        # specialize_kernel: compile (once, cached) a straight-line kernel for this topology (small networks)
+        self.network = graph_data if isinstance(graph_data, Network) else Network(graph_data, specialize=specialize_kernel)
         self.engine = AssignmentEngine(self.network, device, precision, bpr_alpha, bpr_beta, unassigned_penalty,
                                        line_search_iters)
         self.device = self.engine.device

@@ -69,6 +69,7 @@ class RepairEnv:
         seed: int = 0,
         precision: str = "fp32",
         line_search_iters: int = 24,
+        specialize_kernel: bool = False,
     ):
         self.graph_data = graph_data
         self.bpr_alpha, self.bpr_beta = bpr_alpha, bpr_beta
@@ -94,7 +95,8 @@ class RepairEnv:
         self._fixed_damaged_indices = None
         self._fixed_damage_rng = np.random.default_rng(fixed_damage_seed) if fixed_damage_seed is not None else None
 
-        self.network = graph_data if isinstance(graph_data, Network) else Network(graph_data)
+        # specialize_kernel: compile (once, cached) a straight-line kernel for this topology (small networks)
+        self.network = graph_data if isinstance(graph_data, Network) else Network(graph_data, specialize=specialize_kernel)
         net = self.network
         self.num_nodes, self.edges, self.num_edges = net.num_nodes, net.edges, net.num_edges
         self.edge_index = net.edge_index
