@@ -1,3 +1,4 @@
+"""Pretty-print bench.py JSON lines from stdin:  python bench.py | python tools/benchline.py"""
 import sys,json
 for l in sys.stdin:
     if l.startswith("{"):
