@@ -155,6 +155,20 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
     float *graw = (float *)(smem + 128);                                   // [(E+N)][H]
     float *xs = graw + (((size_t)(E + N) * H + 31) & ~(size_t)31);          // staged xw[b]
     float *gs = xs + slab;                                                  // staged grad_out[b]
+    // staged attention terms of the graph: a_src [N][H] | a_dst [N][H] | a_edge [E+N][H] | alpha [E+N][H]
+    const size_t nh = (size_t)N * H, eh = (size_t)(E + N) * H;
+    const bool att_ok = STAGED && (nh * 4) % 16 == 0 && (eh * 4) % 16 == 0;
+    float *att = gs + slab;
+    auto issue_g = [&](int b) {   // thread 0: grad_out slab + attention terms on bar_g
+        mbar_expect_tx(bar + 1, (uint32_t)(slab * 4 + (att_ok ? (2 * nh + 2 * eh) * 4 : 0)));
+        tma_bulk_g2s(gs, p.grad_out + (size_t)b * slab, (uint32_t)(slab * 4), bar + 1);
+        if (att_ok) {
+            tma_bulk_g2s(att, p.a_src + (size_t)b * nh, (uint32_t)(nh * 4), bar + 1);
+            tma_bulk_g2s(att + nh, p.a_dst + (size_t)b * nh, (uint32_t)(nh * 4), bar + 1);
+            tma_bulk_g2s(att + 2 * nh, p.a_edge + (size_t)b * eh, (uint32_t)(eh * 4), bar + 1);
+            tma_bulk_g2s(att + 2 * nh + eh, p.alpha_in + (size_t)b * eh, (uint32_t)(eh * 4), bar + 1);
+        }
+    };
     // two mbarriers: xw is only needed in phase 1, so the next graph's xw is fetched while phase 2
     // still runs on grad_out; only the grad_out copy is exposed at the top of the loop
     uint64_t *bar_x = bar, *bar_g = bar + 1;
@@ -166,8 +180,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
         if (threadIdx.x == 0 && blockIdx.x < p.B) {
             mbar_expect_tx(bar_x, (uint32_t)(slab * 4));
             tma_bulk_g2s(xs, p.xw + (size_t)blockIdx.x * slab, (uint32_t)(slab * 4), bar_x);
-            mbar_expect_tx(bar_g, (uint32_t)(slab * 4));
-            tma_bulk_g2s(gs, p.grad_out + (size_t)blockIdx.x * slab, (uint32_t)(slab * 4), bar_g);
+            issue_g(blockIdx.x);
         }
     }
     int it = 0;
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
         const float *as = p.a_src + (size_t)b * N * H, *ad = p.a_dst + (size_t)b * N * H;
         const float *ae = p.a_edge + (size_t)b * (E + N) * H;
         const float *al = p.alpha_in + (size_t)b * (E + N) * H;
+        if (att_ok) { as = att; ad = att + nh; ae = att + 2 * nh; al = att + 2 * nh + eh; }
         float *g_as = p.grad_a_src + (size_t)b * N * H, *g_ad = p.grad_a_dst + (size_t)b * N * H;
         float *g_ae = p.grad_a_edge + (size_t)b * (E + N) * H;
         float *gx = p.grad_xw + (size_t)b * slab;
@@ -263,10 +277,7 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
             }
         }
         __syncthreads();
-        if (STAGED && threadIdx.x == 0 && b + (int)gridDim.x < p.B) {   // phase 2 is done with grad_out
-            mbar_expect_tx(bar_g, (uint32_t)(slab * 4));
-            tma_bulk_g2s(gs, p.grad_out + (size_t)(b + gridDim.x) * slab, (uint32_t)(slab * 4), bar_g);
-        }
+        if (STAGED && threadIdx.x == 0 && b + (int)gridDim.x < p.B) issue_g(b + gridDim.x);   // phase 2 is done with grad_out
     }
 }
 
@@ -342,8 +353,9 @@ extern "C" int b200_gat_edge_softmax_aggregate_bwd(const b200_graph *g, int B, i
     const size_t slab_bytes = (size_t)g->N * H * C * 4;
     const size_t graw_bytes = ((((size_t)(g->E + g->N) * H + 31) & ~(size_t)31)) * 4;
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem_staged = 128 + graw_bytes + 2 * slab_bytes;
-    if (smem_staged <= 220 * 1024) {
+    const size_t att_bytes = ((size_t)2 * g->N * H + 2 * (size_t)(g->E + g->N) * H) * 4 + 64;
+    const size_t smem_staged = 128 + graw_bytes + 2 * slab_bytes + att_bytes;
+    if (smem_staged <= 226 * 1024) {
         B200_CUDA(cudaFuncSetAttribute(gat_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_staged));
         int per_sm = 0;
         B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gat_bwd_kernel<true>, gat_threads(g->N, H), smem_staged));
