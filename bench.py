@@ -11,10 +11,15 @@ One "step" = one batched compute_flow_assignment over the whole batch (= 4096 as
 Multi-GPU: scenarios are independent, every rank solves its own 4096 (weak scaling, no
 data-path collective); value = all ranks' assignments / max-over-ranks device time.
 
-`--impl reference` times the CPU restatement of the reference path (oracle/ref_port.py: the
-reference's own numpy + scipy.csgraph.dijkstra + Python predecessor walk, one env per process,
-all host cores - the structure of the reference's rollout workers / run_multiseed) on a bounded
-sample of the same workload.  The reference itself is Python and cannot travel to the GPU box.
+`--impl reference` times the REFERENCE ITSELF: its unmodified `src.env.repair_env.RepairEnv`
+(`sp_backend="scipy", use_torch=False` - numpy BPR + scipy.csgraph.dijkstra + Python predecessor
+walk), imported from the verbatim copy in oracle/_ref/ (made by oracle/fetch_ref.py; git-ignored, it
+travels to the GPU box with the snapshot), one env per process on all host cores - the structure of
+the reference's rollout workers / run_multiseed - on a bounded sample of the same workload
+(`cpu_baseline.kind = "reference"`).  Only if that copy is missing does it fall back to the numpy/scipy
+restatement oracle/ref_port.py (`kind = "port"`).  `cpu_baseline_ref_gpu` is the reference's own GPU
+path (`sp_backend="torch", use_torch=True, device="cuda"`: dense Floyd-Warshall in torch,
+src/env/repair_env.py:520-573) on the same B200.
 """
 from __future__ import annotations
 
@@ -138,6 +143,78 @@ def _port_worker(args):
     return time.perf_counter() - t0, acc
 
 
+def _draw_masks(seed0: int, n: int, row=None, col=None, num_nodes: int = 24):
+    """n damage masks of the bench workload, drawn on the host with the reference's rule (reset,
+    src/env/repair_env.py:167-190: 22 of 76 links, retry until the undamaged links form a strongly
+    connected subgraph).  Self-contained (numpy + scipy) so that the reference arm imports nothing of
+    the product package."""
+    from scipy.sparse import csr_matrix
+    from scipy.sparse.csgraph import connected_components
+    E = int(row.shape[0])
+    k = max(1, int(E * 0.3))
+    rng = np.random.default_rng(seed0)
+    masks = np.zeros((n, E), np.uint8)
+    for i in range(n):
+        cand = None
+        for _ in range(50):
+            cand = rng.choice(E, size=k, replace=False)
+            act = np.ones(E, bool)
+            act[cand] = False
+            nodes = np.unique(np.concatenate([row[act], col[act]]))
+            sub = csr_matrix((np.ones(int(act.sum())), (row[act], col[act])), shape=(num_nodes, num_nodes))
+            _, labels = connected_components(sub, directed=True, connection="strong")
+            if np.unique(labels[nodes]).size == 1:
+                break
+        masks[i, cand] = 1
+    return masks
+
+
+def _reference_worker(args):
+    """One process = one reference RepairEnv (its CPU path), n cold-start compute_flow_assignment()."""
+    seed0, n_assign, k_iters, method = args
+    from oracle import reference_env as R
+    env = R.make_env(assignment_method=method, assignment_iters=k_iters, damaged_ratio=0.3, seed=seed0)
+    masks = _draw_masks(seed0, n_assign, env.edge_index[0], env.edge_index[1], env.num_nodes)
+    wall = R.time_assignments(env, masks)
+    return wall, float(env.tstt)
+
+
+def _reference_available() -> bool:
+    from oracle import reference_env as R
+    return R.available()
+
+
+def cpu_reference_rate(n_per_proc: int, procs: int) -> dict:
+    """Aggregate assignments/s of the unmodified reference env, one env per process (spawned, like
+    the reference's rollout workers src/train.py:138-214 / scripts/run_multiseed.py:37-38)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        pool.map(_reference_worker, [(1, 1, 2, METHOD)] * procs)  # import + warm-up
+        t0 = time.perf_counter()
+        pool.map(_reference_worker, [(5000 + i, n_per_proc, ASSIGN_ITERS, METHOD) for i in range(procs)])
+        wall = time.perf_counter() - t0
+    n = n_per_proc * procs
+    return {"value": n / wall, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": f"{n} cold-start Sioux Falls {METHOD} K={ASSIGN_ITERS} assignments, {procs} processes x "
+                      f"{n_per_proc}, the reference's own RepairEnv.compute_flow_assignment (oracle/_ref copy of "
+                      f"src/env/repair_env.py, sp_backend=scipy, use_torch=False), wall {wall:.1f}s"}
+
+
+def reference_gpu_rate(n_assign: int = 12) -> dict:
+    """The reference's own GPU path on this box's GPU: torch BPR + dense torch Floyd-Warshall
+    (src/env/repair_env.py:520-573, :679-705; the setup of the reference's test_env_gpu.py:22-31)."""
+    from oracle import reference_env as R
+    env = R.make_env(assignment_method=METHOD, assignment_iters=ASSIGN_ITERS, damaged_ratio=0.3, seed=5000,
+                     sp_backend="torch", use_torch=True, device="cuda", force_gpu_sp=True)
+    masks = _draw_masks(5000, n_assign + 1, env.edge_index[0], env.edge_index[1], env.num_nodes)
+    R.time_assignments(env, masks[:1])
+    wall = R.time_assignments(env, masks[1:])
+    return {"value": n_assign / wall, "unit": UNIT, "kind": "reference-gpu", "gpus": 1,
+            "sample": f"{n_assign} cold-start Sioux Falls {METHOD} K={ASSIGN_ITERS} assignments, one reference "
+                      f"RepairEnv(sp_backend='torch', use_torch=True, device='cuda', force_gpu_sp=True), wall {wall:.1f}s"}
+
+
 def cpu_port_rate(n_per_proc: int, procs: int) -> dict:
     """Aggregate assignments/s of the numpy/scipy restatement, one env per process."""
     import multiprocessing as mp
@@ -179,7 +256,8 @@ def run_reference_arm(args) -> None:
     procs = os.cpu_count() or 1
     per_step = 2  # assignments per process per "step": bounded sample
     total_steps = args.steps + args.warmup
-    res = cpu_port_rate(per_step * max(total_steps, 1), procs)
+    rate = cpu_reference_rate if _reference_available() else cpu_port_rate
+    res = rate(per_step * max(total_steps, 1), procs)
     n_per_step = per_step * procs
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -296,7 +374,10 @@ def run_ours(args) -> None:
     gap_med = float(env.gap.median().item())
     tstt_chk = float(env.tstt.sum().item())
 
-    other = None if args.no_extra else measure_other_configs(b200env, torch, dist, dev, rank, world, measured_peak()[0])
+    other = None
+    if not args.no_extra:
+        other = measure_sf_extras(b200env, torch, dist, dev, rank, world, g, masks, measured_peak()[0])
+        other.update(measure_other_configs(b200env, torch, dist, dev, rank, world, measured_peak()[0]))
     if rank == 0:
         peak, peak_src = measured_peak()
         kern_s = statistics.mean(kern_ms) / 1e3
@@ -323,12 +404,121 @@ def run_ours(args) -> None:
         line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             procs = os.cpu_count() or 1
-            # ~0.1 s per assignment per core -> 100 per process is a 10-20 s bounded sample
-            line["cpu_baseline"] = cpu_port_rate(100, procs)
+            # ~0.1-0.2 s per assignment per core -> 100 per process is a 10-30 s bounded sample
+            if _reference_available():
+                line["cpu_baseline"] = cpu_reference_rate(100, procs)
+                try:
+                    line["cpu_baseline_ref_gpu"] = reference_gpu_rate()
+                except Exception as exc:  # noqa: BLE001 - informational leg
+                    line["cpu_baseline_ref_gpu"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
+            else:
+                line["cpu_baseline"] = cpu_port_rate(100, procs)
             line["cpu_baseline_c_oracle"] = c_oracle_rate()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(torch, dist, dev, world: int, value: float) -> float:
+    t = torch.tensor([value], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_sf_extras(b200env, torch, dist, dev, rank: int, world: int, g, masks, peak: float) -> dict:
+    """Sioux Falls figures beyond the headline launch (all CUDA-event timed, max over ranks):
+    the WHOLE env step, the north star's target configuration (4096 scenarios in TOTAL, sharded over
+    the ranks = strong scaling), the line-search extension, and the end-to-end call with the link
+    flows copied back to the host as well."""
+    out = {}
+    B, E = masks.shape
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, reps: int):
+        ms = []
+        for _ in range(reps):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sync()
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize(dev)
+            ms.append(_max_over_ranks(torch, dist, dev, world, s.elapsed_time(e)))
+        return ms
+
+    # ---- one full BatchedRepairEnv.step: apply actions + warm-start assignment + reward/done + state features
+    env = b200env.BatchedRepairEnv(g, B, assignment_method=METHOD, assignment_iters=ASSIGN_ITERS, device=dev,
+                                   precision="fp32")
+    env.reset(damage_masks=masks)
+    order = np.argsort(-masks.astype(np.int8), axis=1, kind="stable")[:, :22]      # the damaged links, ascending
+    acts = torch.from_numpy(np.ascontiguousarray(order.T.astype(np.int32))).to(dev)  # [22, B]: one valid repair per step
+    for i in range(3):
+        env.step(acts[i], validate_actions=False)
+    l0 = env.engine.launches
+    step_ms = []
+    for i in range(3, 19):
+        step_ms += timed(lambda i=i: env.step(acts[i], validate_actions=False), 1)
+    ms = statistics.mean(step_ms)
+    out["sf_step_4096"] = {"env_steps_per_s": B * world / ms * 1e3, "ms_per_step": ms, "steps_timed": len(step_ms),
+                           "scenarios_per_gpu": B, "scaling": "weak", "launches_per_step": (env.engine.launches - l0) / 16,
+                           "what": "BatchedRepairEnv.step: apply_actions + fused warm-start fw K=20 assignment + "
+                                   "reward/done + state features (Brandes betweenness) + returned copies"}
+    del env
+
+    eng = b200env.AssignmentEngine(b200env.Network(g), dev, "fp32")
+    bytes_per = ASSIGN_ITERS * (33 * eng.E + 8 * eng.O * eng.N)
+
+    # ---- the target configuration: 4096 scenarios in total, sharded over the ranks
+    lo, hi = B * rank // world, B * (rank + 1) // world
+    dmg = torch.from_numpy(masks[lo:hi]).to(dev)
+    flow = torch.zeros((hi - lo, E), dtype=torch.float32, device=dev)
+    eng.assign(dmg, flow, ASSIGN_ITERS, METHOD)
+
+    def strong():
+        flow.zero_()
+        eng.assign(dmg, flow, ASSIGN_ITERS, METHOD)
+    ms = min(timed(strong, 5))
+    out["sf_fw_4096_total_strong"] = {"assignments_per_s": B / ms * 1e3, "ms_per_launch": ms, "scenarios_total": B,
+                                      "scenarios_per_gpu": hi - lo, "scaling": "strong",
+                                      "roofline_frac_per_gpu": bytes_per * (hi - lo) / (ms / 1e3) / 1e9 / peak}
+
+    # ---- fw with the bisection line search (north-star extension): rate and the gap it buys
+    dmg_all = torch.from_numpy(masks).to(dev)
+    flow_all = torch.zeros((B, E), dtype=torch.float32, device=dev)
+    res = {}
+
+    def fw_ls():
+        flow_all.zero_()
+        res["r"] = eng.assign(dmg_all, flow_all, ASSIGN_ITERS, "fw_ls")
+    fw_ls()
+    ms = min(timed(fw_ls, 3))
+    out["sf_fw_ls_4096"] = {"assignments_per_s": B * world / ms * 1e3, "ms_per_launch": ms, "scaling": "weak",
+                            "line_search_iters": eng.ls_iters,
+                            "median_relative_gap_at_K": float(res["r"]["gap"].median().item())}
+    del eng
+
+    # ---- end to end with the link flows returned as well (masks in; TSTT + flows out)
+    env = b200env.BatchedRepairEnv(g, B, assignment_method=METHOD, assignment_iters=ASSIGN_ITERS, device=dev,
+                                   precision="fp32")
+    pinned = torch.from_numpy(masks).pin_memory()
+    out_t, out_f = np.empty(B, np.float64), np.empty((B, E), np.float32)
+    for _ in range(2):
+        env.assign_host(pinned.numpy(), out_t, out_f)
+    sync()
+    reps = 20
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        env.assign_host(pinned.numpy(), out_t, out_f)
+    wall = _max_over_ranks(torch, dist, dev, world, time.perf_counter() - t0)
+    out["e2e_flows"] = {"value": B * world * reps / wall, "unit": UNIT, "h2d_bytes_per_step": int(B * E),
+                        "d2h_bytes_per_step": int(B * 8 + B * E * 4), "steps": reps}
+    del env
+    return out
 
 
 def measure_other_configs(b200env, torch, dist, dev, rank: int, world: int, peak: float) -> dict:

@@ -97,6 +97,11 @@ int b200_assign(const b200_graph *g, int B, int prec, int K, int method, const u
 
 /* How many kernels the last b200_assign on this handle launched (for bench.py's gpu_launches). */
 int b200_assign_launches(const b200_graph *g);
+/* Launch configuration of the last b200_assign on this handle: cfg[0] = kernels launched, cfg[1] =
+ * thread-block cluster size (1 = one CTA per scenario), cfg[2] = 1 when iterations after the first
+ * warm-started their shortest paths from the previous trees, cfg[3] = warps per CTA.  Parity tests
+ * use it to prove that the path they mean to cover (cluster mode, warm start) is the one that ran. */
+int b200_assign_last_config(const b200_graph *g, int32_t cfg[4]);
 /* Which fused kernel b200_assign dispatches to for this network ("assign_static_kernel",
  * "assign_small_kernel" or "assign_fused_kernel"; static string). */
 const char *b200_assign_kernel_name(const b200_graph *g);

@@ -26,11 +26,11 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
-# every symbol include/b200_assign.h declares (checked by tests/test_abi.py)
+# every symbol include/b200_assign.h declares (tests/test_host.py::test_c_abi_library_loads_and_exports_header_symbols)
 EXPORTS = [
     "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
     "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
-    "b200_assign_launches", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_assign_launches", "b200_assign_last_config", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
     "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
 ]
 
@@ -117,6 +117,7 @@ def _declare(lib) -> None:
                                        _i, _vp]
     lib.b200_assign.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp]
     lib.b200_assign_launches.argtypes = [_vp]
+    lib.b200_assign_last_config.argtypes = [_vp, _vp]
     lib.b200_assign_kernel_name.argtypes = [_vp]
     lib.b200_register_static_plugin.argtypes = [C.c_char_p]
     lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]

@@ -883,6 +883,7 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
         }
         p.tree_ws = gm->tree_ws;
         gm->last_cluster = cluster;
+        gm->last_warps = warps;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);

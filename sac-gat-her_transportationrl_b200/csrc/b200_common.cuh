@@ -65,6 +65,7 @@ struct b200_graph {
     int group_lanes;     // lanes per origin group in the general fused kernel (8 or 32; env B200_GROUP)
     int cluster_limit;   // max thread-block cluster size of the general kernel (env B200_CLUSTER; 1 = off, 0 = auto)
     int last_cluster;    // cluster size of the last fused launch (tests / tools)
+    int last_warps;      // warps per CTA of the last fused launch
     // per-link attributes, TNTP order
     int32_t *row, *col;
     float *t0, *cap0;

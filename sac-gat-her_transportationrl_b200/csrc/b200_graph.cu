@@ -238,6 +238,17 @@ extern "C" int b200_graph_origins(const b200_graph *g, int32_t *origins_host)
 
 extern "C" int b200_assign_launches(const b200_graph *g) { return g ? g->last_launches : 0; }
 
+extern "C" int b200_assign_last_config(const b200_graph *g, int32_t cfg[4])
+{
+    B200_REQUIRE(g && cfg, "null argument");
+    const bool general = !(g->static_ok && !g->force_general && !g->force_small) && !(g->small_ok && !g->force_general);
+    cfg[0] = g->last_launches;
+    cfg[1] = general ? std::max(g->last_cluster, 1) : 1;
+    cfg[2] = general ? g->warm_start : 0;
+    cfg[3] = general ? g->last_warps : 0;
+    return 0;
+}
+
 extern "C" const char *b200_assign_kernel_name(const b200_graph *g)
 {
     if (!g) return "";

@@ -58,7 +58,10 @@ class AssignmentEngine:
         self.real = torch.float32 if self.prec == 0 else torch.float64
         self.net = network
         if network.device_index != (self.device.index or 0):
-            network.close()
+            if network._handle is not None:
+                # the handle may be shared (another engine, a GAT module): never free it here
+                raise ValueError(f"Network already lives on cuda:{network.device_index}; build another Network "
+                                 f"for {self.device}")
             network.device_index = self.device.index or 0
         self.alpha, self.beta = float(bpr_alpha), float(bpr_beta)
         self.penalty, self.ls_iters = float(unassigned_penalty), int(line_search_iters)
@@ -72,6 +75,14 @@ class AssignmentEngine:
     def kernel_name(self) -> str:
         """Which fused kernel ``assign`` dispatches to for this network."""
         return self.lib.b200_assign_kernel_name(self.h).decode()
+
+    @property
+    def last_config(self) -> Dict[str, int]:
+        """Launch configuration of the last ``assign`` (kernels, cluster size, warm start, warps per CTA)."""
+        import ctypes as C
+        cfg = (C.c_int32 * 4)()
+        _native.check(self.lib.b200_assign_last_config(self.h, cfg), "b200_assign_last_config")
+        return dict(launches=cfg[0], cluster=cfg[1], warm=cfg[2], warps=cfg[3])
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
@@ -308,12 +319,25 @@ class BatchedRepairEnv:
         self.assignments_done += self.B
         return self.tstt
 
-    def step(self, actions) -> Tuple[BatchedEnvState, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    def step(self, actions, validate_actions: bool = True
+             ) -> Tuple[BatchedEnvState, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+        """One lock-step env step.  Out-of-range actions raise ``ValueError`` BEFORE anything is mutated,
+        like the reference (:208-209): host-side actions (list / numpy / CPU tensor) are checked on the
+        host at no cost; a CUDA tensor is checked with one device reduction (a stream sync) unless
+        ``validate_actions=False`` - callers whose actions are in range by construction (a masked
+        categorical over the E links, the trainer) pass False and keep the hot loop free of syncs; an
+        out-of-range row then counts as an invalid action (reward -1, scenario untouched) and is
+        reported in ``info["out_of_range"]``."""
         if not isinstance(actions, torch.Tensor):
-            actions = torch.as_tensor(np.asarray(actions), dtype=torch.int32)
-        actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
+            actions = torch.as_tensor(np.asarray(actions))
         if actions.shape != (self.B,):
             raise ValueError(f"actions must have shape ({self.B},)")
+        if validate_actions or actions.device.type == "cpu":
+            bad = (actions < 0) | (actions >= self.E)
+            if bool(bad.any()):
+                b = int(torch.nonzero(bad)[0])
+                raise ValueError(f"action_edge_id {int(actions[b])} out of range (0..{self.E - 1})")
+        actions = actions.to(device=self.device, dtype=torch.int32).contiguous()
         eng, lib = self.engine, self.engine.lib
         self._prev_tstt.copy_(self.tstt)
         self._act_status.zero_()
@@ -328,11 +352,9 @@ class BatchedRepairEnv:
             float(self.reward_alpha), float(self.reward_beta), float(self.reward_gamma), float(self.reward_clip or 0.0),
             _ptr(self._reward), _ptr(self._done), eng._stream()), "b200_reward_done")
         eng.launches += 2
-        if bool((self._act_status != 0).any()):
-            bad = int(torch.nonzero(self._act_status)[0])
-            raise ValueError(f"action_edge_id {int(actions[bad])} out of range (0..{self.E - 1})")
         state = self.get_state()
-        return state, self._reward.clone(), self._done.bool(), {"tstt": self.tstt.clone(), "valid": self._valid.bool()}
+        return state, self._reward.clone(), self._done.bool(), {"tstt": self.tstt.clone(), "valid": self._valid.bool(),
+                                                                "out_of_range": self._act_status != 0}
 
     def get_state(self) -> BatchedEnvState:
         node, edge = self.engine.state_features(self.flow, self.is_damaged, self.goal_mask, self.tstt,
@@ -343,9 +365,11 @@ class BatchedRepairEnv:
                                goal_mask=self.goal_mask.to(torch.float32))
 
     # ---- end-to-end host entry point (bench.py's e2e leg, greedy baseline) --------------------
-    def assign_host(self, damage_masks: np.ndarray, out_tstt: Optional[np.ndarray] = None) -> np.ndarray:
+    def assign_host(self, damage_masks: np.ndarray, out_tstt: Optional[np.ndarray] = None,
+                    out_flow: Optional[np.ndarray] = None) -> np.ndarray:
         """Host buffers in, host buffers out: H2D of the uint8 masks, cold-start assignment,
-        D2H of TSTT.  ``damage_masks`` [B,E] uint8 (pinned memory recommended)."""
+        D2H of TSTT (and of the link flows when ``out_flow`` [B,E] is given - the reference leaves
+        ``flow`` on the host too, :335).  ``damage_masks`` [B,E] uint8 (pinned memory recommended)."""
         src = torch.from_numpy(damage_masks) if isinstance(damage_masks, np.ndarray) else damage_masks
         self.is_damaged.copy_(src, non_blocking=True)
         self.flow.zero_()
@@ -353,7 +377,13 @@ class BatchedRepairEnv:
         if not hasattr(self, "_pinned_tstt"):
             self._pinned_tstt = torch.empty((self.B,), dtype=torch.float64).pin_memory()
         self._pinned_tstt.copy_(self.tstt, non_blocking=True)
+        if out_flow is not None:
+            if not hasattr(self, "_pinned_flow"):
+                self._pinned_flow = torch.empty((self.B, self.E), dtype=self.engine.real).pin_memory()
+            self._pinned_flow.copy_(self.flow, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        if out_flow is not None:
+            out_flow[:] = self._pinned_flow.numpy()
         res = self._pinned_tstt.numpy()
         if out_tstt is not None:
             out_tstt[:] = res

@@ -214,3 +214,54 @@ def test_batched_episode_runner_and_simple_policies(b200env, native_lib, sf_grap
         assert pol(st).shape == (B,)
     stuck = bl.run_episode(benv, lambda s: torch.zeros(B, dtype=torch.int32, device="cuda:0"), max_steps=3)
     assert stuck["tstt_curve"].shape[0] == 3  # a policy that never finishes stops at max_steps
+
+
+@pytest.mark.parametrize("which", ["an", "cs"])
+def test_state_features_large_networks_vs_oracle_betweenness(b200env, native_lib, which):
+    """`features_kernel` beyond Sioux Falls: node feature 0 (Brandes betweenness of the undamaged
+    subgraph / its maximum, reference src/env/repair_env.py:753-770) and the remaining node / link
+    features against the C oracle's `orc_betweenness` and the reference's formulas (:771-807) for 8
+    damage draws on the Anaheim-size network (3 on the Chicago-Sketch-size one)."""
+    from oracle.c_oracle import COracle
+    g = b200env.synthetic.anaheim_size(0) if which == "an" else b200env.synthetic.chicago_sketch_size(0)
+    orc = COracle.from_graph_data(g)
+    net = b200env.Network(g)
+    eng = b200env.AssignmentEngine(net, "cuda:0", "fp32")
+    B = 8 if which == "an" else 3
+    E, N = eng.E, eng.N
+    rng = np.random.default_rng(31)
+    dmg = np.zeros((B, E), np.uint8)
+    for b in range(B):
+        dmg[b, rng.choice(E, int(E * 0.3), replace=False)] = 1
+    dmg[0] = 0                                                     # the undamaged network too
+    flow = (rng.random((B, E)) * 9000.0).astype(np.float32)
+    goal = dmg.copy()
+    goal[:, ::7] = 0
+    tstt = rng.random(B) * 500.0 + 2.0
+    d = torch.device("cuda", 0)
+    node, edge, raw = eng.state_features(torch.from_numpy(flow).to(d), torch.from_numpy(dmg).to(d),
+                                         torch.from_numpy(goal).to(d), torch.from_numpy(tstt).to(d), 1e-3,
+                                         return_raw_betweenness=True)
+    node, edge, raw = node.cpu().numpy(), edge.cpu().numpy(), raw.cpu().numpy()
+    row, col = net.edge_index
+    cap0, t0 = net.initial_capacities, net.t0
+    for b in range(B):
+        bw = orc.betweenness(dmg[b])
+        np.testing.assert_allclose(raw[b], bw, rtol=2e-5, atol=1e-9)
+        mx = bw.max()
+        np.testing.assert_allclose(node[b, :, 0], bw / mx if mx > 0 else bw, rtol=2e-5, atol=1e-7)
+        # remaining_ratio, avg_flow_norm, log10 TSTT (reference :771-790)
+        cap = np.where(dmg[b] > 0, np.float32(1e-3), cap0)
+        remaining = float(np.sum(goal[b].astype(np.float32) * dmg[b])) / max(float(goal[b].sum()), 1.0)
+        avg_flow = float(np.mean(flow[b][dmg[b] == 0])) / max(net.total_demand / max(E, 1), 1.0)
+        np.testing.assert_allclose(node[b, :, 1], np.float32(remaining), rtol=1e-6)
+        np.testing.assert_allclose(node[b, :, 2], np.float32(avg_flow), rtol=1e-5)
+        np.testing.assert_allclose(node[b, :, 3], np.float32(np.log10(max(tstt[b], 1.0))), rtol=1e-6)
+        # link features (reference :792-807)
+        exp_e = np.stack([
+            np.log10(t0 + 1.0) / np.log10(net.max_t0 + 1.0),
+            np.log10(cap + 1.0) / np.log10(net.max_capacity + 1.0),
+            np.where(dmg[b] > 0, 0.0, np.clip(np.log1p(flow[b] / np.maximum(cap, 1e-6)), 0.0, 10.0)),
+            dmg[b].astype(np.float32), goal[b].astype(np.float32),
+            np.arange(E, dtype=np.float32) / max(E - 1, 1)], axis=1)
+        np.testing.assert_allclose(edge[b], exp_e, rtol=1e-4, atol=2e-6)

@@ -531,3 +531,100 @@ def test_fractional_demand_uses_float_scatter_add(b200env, native_lib, sf_graph)
             o = orc.assign(masks[b], None, 20, "fw", dtype=dtype)
             np.testing.assert_allclose(out["flow"][b], o["flow"], rtol=rtol, atol=rtol * 10)
             assert abs(out["tstt"][b] - o["tstt"]) / o["tstt"] <= rtol
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-level parity at the BENCHMARKED sizes of the large networks (BASELINE.json configs 3 / 4):
+# K = 20, the warm-started trees of iterations >= 1, thread-block-cluster mode for the shards of an
+# 8-GPU run, fw on the Chicago-Sketch-size network.  Integer demands => int32 link loads => every
+# path must reproduce the C oracle bit for bit (reference loop: src/env/repair_env.py:299-345,
+# all-or-nothing loading :481-503).
+# ---------------------------------------------------------------------------------------------
+def _damage_batch(E, B, seed, ratio=0.3):
+    rng = np.random.default_rng(seed)
+    masks = np.zeros((B, E), np.uint8)
+    for b in range(B):
+        masks[b, rng.choice(E, max(1, int(E * ratio)), replace=False)] = 1
+    return masks
+
+
+def _assert_bit_equal_to_oracle(out, orc, masks, rows, K, method, tag):
+    for b in rows:
+        o = orc.assign(masks[b], None, K, method)
+        assert np.array_equal(out["flow"][b], o["flow"]), f"{tag}: flows of scenario {b} differ from the C oracle"
+        assert out["tstt"][b] == o["tstt"], f"{tag}: TSTT of scenario {b}"
+        assert out["unassigned"][b] == o["unassigned"], f"{tag}: unassigned demand of scenario {b}"
+        np.testing.assert_allclose(out["gap"][b], o["gap"], rtol=1e-9, err_msg=f"{tag}: gap of scenario {b}")
+
+
+@pytest.mark.parametrize("method", ["fw", "msa"])
+def test_anaheim_size_k20_bit_exact_vs_oracle_default_nowarm_cluster(b200env, native_lib, monkeypatch, method):
+    """Config 3 as benchmarked (K = 20, cold start), 64 scenarios, every 4th against the C oracle, run
+    three ways: the default dispatch, warm start forced the other way, and a 16-scenario shard (what
+    one rank of an 8-GPU run of 128 scenarios gets), which must take thread-block-cluster mode."""
+    from oracle.c_oracle import COracle
+    g = b200env.synthetic.anaheim_size(0)
+    orc = COracle.from_graph_data(g)
+    B, K = 64, 20
+    masks = _damage_batch(len(g.edges), B, seed=2024)
+    default = _engine(b200env, g, "fp32")
+    out = _assign(default, masks, K, method)
+    cfg = default.last_config
+    assert default.kernel_name == "assign_fused_kernel" and cfg["cluster"] == 1, cfg
+    assert np.all(out["status"] == 0)
+    _assert_bit_equal_to_oracle(out, orc, masks, range(0, B, 4), K, method, "default")
+    # the other shortest-path start (the default for this network is decided by links/node)
+    monkeypatch.setenv("B200_NO_WARM" if cfg["warm"] else "B200_WARM", "1")
+    other = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_NO_WARM" if cfg["warm"] else "B200_WARM")
+    out2 = _assign(other, masks, K, method)
+    assert other.last_config["warm"] == 1 - cfg["warm"]
+    assert np.array_equal(out2["flow"], out["flow"]) and np.array_equal(out2["tstt"], out["tstt"])
+    _assert_bit_equal_to_oracle(out2, orc, masks, range(1, B, 16), K, method, "other start")
+    # 16-scenario shard -> cluster mode
+    out3 = _assign(default, masks[:16], K, method)
+    assert default.last_config["cluster"] > 1, default.last_config
+    assert np.array_equal(out3["flow"], out["flow"][:16]) and np.array_equal(out3["tstt"], out["tstt"][:16])
+    _assert_bit_equal_to_oracle(out3, orc, masks, range(0, 16, 4), K, method, "cluster")
+
+
+@pytest.mark.parametrize("method", ["fw", "msa"])
+def test_chicago_sketch_size_k20_bit_exact_vs_oracle_incl_cluster(b200env, native_lib, method):
+    """Config 4 as benchmarked: K = 20, msa AND fw, 8 scenarios against the C oracle (2 s each on the
+    host); the same scenarios again as two 4-scenario launches, which take cluster mode (an 8-GPU run of
+    256 scenarios gives each rank 32 < 148 SMs)."""
+    from oracle.c_oracle import COracle
+    g = b200env.synthetic.chicago_sketch_size(0)
+    orc = COracle.from_graph_data(g)
+    B, K = 8, 20
+    masks = _damage_batch(len(g.edges), B, seed=77)
+    eng = _engine(b200env, g, "fp32")
+    out = _assign(eng, masks, K, method)
+    cfg = eng.last_config
+    assert eng.kernel_name == "assign_fused_kernel" and np.all(out["status"] == 0)
+    _assert_bit_equal_to_oracle(out, orc, masks, range(B), K, method, f"B=8 (cluster {cfg['cluster']}, warm {cfg['warm']})")
+    big = _assign(eng, np.concatenate([masks] * 40), K, method)     # 320 scenarios > resident CTAs: no cluster
+    assert eng.last_config["cluster"] == 1
+    assert np.array_equal(big["flow"][:B], out["flow"]) and np.array_equal(big["flow"][-B:], out["flow"])
+    for lo in (0, 4):
+        part = _assign(eng, masks[lo:lo + 4], K, method)
+        assert eng.last_config["cluster"] > 1, eng.last_config
+        assert np.array_equal(part["flow"], out["flow"][lo:lo + 4]) and np.array_equal(part["tstt"], out["tstt"][lo:lo + 4])
+
+
+def test_sf_4096_flip_report(b200env, native_lib, sf_graph, golden, capsys):
+    """The 4096-scenario comparison with the reference tolerates a handful of near-tie flips (the
+    reference's numpy powf is not correctly rounded); this test REPORTS how many occurred and which
+    scenario is worst, for both precisions, and pins the count to what was measured."""
+    G = golden("sf_batch4096_fw_k20.npz")
+    masks = _masks_from_idx(G["dmg"], 76)
+    report = {}
+    for precision, rtol in (("fp32", RTOL_F32), ("fp64", RTOL_F64)):
+        out = _assign(_engine(b200env, sf_graph, precision), masks, 20, "fw")
+        err = np.abs(out["tstt"] - G["tstt_reset"]) / G["tstt_reset"]
+        worst = int(np.argmax(err))
+        report[precision] = dict(flips=int((err > rtol).sum()), worst_scenario=worst, worst_rel_err=float(err[worst]),
+                                 median_rel_err=float(np.median(err)))
+    with capsys.disabled():
+        print(f"\n[sf_4096_flip_report] {report}")
+    assert report["fp32"]["flips"] <= 4 and report["fp64"]["flips"] <= 4
