@@ -567,21 +567,26 @@ def test_anaheim_size_k20_bit_exact_vs_oracle_default_nowarm_cluster(b200env, na
     orc = COracle.from_graph_data(g)
     B, K = 64, 20
     masks = _damage_batch(len(g.edges), B, seed=2024)
+    monkeypatch.setenv("B200_CLUSTER", "1")
+    single = _engine(b200env, g, "fp32")                                   # one CTA per scenario, whatever B
+    monkeypatch.delenv("B200_CLUSTER")
     default = _engine(b200env, g, "fp32")
-    out = _assign(default, masks, K, method)
-    cfg = default.last_config
-    assert default.kernel_name == "assign_fused_kernel" and cfg["cluster"] == 1, cfg
+    out = _assign(single, masks, K, method)
+    cfg = single.last_config
+    assert single.kernel_name == "assign_fused_kernel" and cfg["cluster"] == 1, cfg
     assert np.all(out["status"] == 0)
-    _assert_bit_equal_to_oracle(out, orc, masks, range(0, B, 4), K, method, "default")
+    _assert_bit_equal_to_oracle(out, orc, masks, range(0, B, 4), K, method, "one CTA per scenario")
     # the other shortest-path start (the default for this network is decided by links/node)
+    monkeypatch.setenv("B200_CLUSTER", "1")
     monkeypatch.setenv("B200_NO_WARM" if cfg["warm"] else "B200_WARM", "1")
     other = _engine(b200env, g, "fp32")
     monkeypatch.delenv("B200_NO_WARM" if cfg["warm"] else "B200_WARM")
+    monkeypatch.delenv("B200_CLUSTER")
     out2 = _assign(other, masks, K, method)
     assert other.last_config["warm"] == 1 - cfg["warm"]
     assert np.array_equal(out2["flow"], out["flow"]) and np.array_equal(out2["tstt"], out["tstt"])
     _assert_bit_equal_to_oracle(out2, orc, masks, range(1, B, 16), K, method, "other start")
-    # 16-scenario shard -> cluster mode
+    # 16-scenario shard with the default dispatch -> cluster mode
     out3 = _assign(default, masks[:16], K, method)
     assert default.last_config["cluster"] > 1, default.last_config
     assert np.array_equal(out3["flow"], out["flow"][:16]) and np.array_equal(out3["tstt"], out["tstt"][:16])
