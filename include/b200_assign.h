@@ -99,9 +99,11 @@ int b200_assign(const b200_graph *g, int B, int prec, int K, int method, const u
 int b200_assign_launches(const b200_graph *g);
 /* Launch configuration of the last b200_assign on this handle: cfg[0] = kernels launched, cfg[1] =
  * thread-block cluster size (1 = one CTA per scenario), cfg[2] = 1 when iterations after the first
- * warm-started their shortest paths from the previous trees, cfg[3] = warps per CTA.  Parity tests
- * use it to prove that the path they mean to cover (cluster mode, warm start) is the one that ran. */
-int b200_assign_last_config(const b200_graph *g, int32_t cfg[4]);
+ * warm-started their shortest paths from the previous trees, cfg[3] = warps per CTA, cfg[4] = 1 when
+ * shortest paths came from the contraction-hierarchy sweeps (exactly summable fp32 costs) rather
+ * than from label correcting, cfg[5..7] reserved (0).  Parity tests use it to prove that the path
+ * they mean to cover (cluster mode, warm start, hierarchy) is the one that ran. */
+int b200_assign_last_config(const b200_graph *g, int32_t cfg[8]);
 /* Which fused kernel b200_assign dispatches to for this network ("assign_static_kernel",
  * "assign_small_kernel" or "assign_fused_kernel"; static string). */
 const char *b200_assign_kernel_name(const b200_graph *g);

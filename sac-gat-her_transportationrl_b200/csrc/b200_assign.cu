@@ -1011,6 +1011,7 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
     B200_REQUIRE(K > 0, "assignment_iters must be > 0 to update TSTT.");
     B200_REQUIRE(method >= B200_MSA && method <= B200_FW_LS, "unknown assignment method");
     const_cast<b200_graph *>(g)->last_launches = 0;
+    const_cast<b200_graph *>(g)->last_cch = 0;
     if (B == 0) return 0;  // empty batch: nothing to do, pointers may be null
     B200_REQUIRE(dmg && flow && tstt && gap && unassigned && status, "null array argument");
     B200_REQUIRE(method != B200_CFW || dprev, "cfw needs the dprev scratch array");

@@ -9,7 +9,7 @@
 
 #include "../../include/b200_assign.h"
 
-#define B200_VERSION 100
+#define B200_VERSION 200
 
 // ---------------------------------------------------------------------------------------------
 // error plumbing
@@ -66,6 +66,7 @@ struct b200_graph {
     int cluster_limit;   // max thread-block cluster size of the general kernel (env B200_CLUSTER; 1 = off, 0 = auto)
     int last_cluster;    // cluster size of the last fused launch (tests / tools)
     int last_warps;      // warps per CTA of the last fused launch
+    int last_cch;        // 1 when the last b200_assign took its shortest paths from the contraction hierarchy
     // per-link attributes, TNTP order
     int32_t *row, *col;
     float *t0, *cap0;
@@ -77,7 +78,8 @@ struct b200_graph {
     float *od_q32;
     // out-link CSR (used by the state-feature BFS) and GAT incoming lists incl. self loops
     int32_t *out_ptr, *out_dst, *out_eid;
-    float max_t0, max_cap0;
+    float max_t0, max_cap0, min_t0;
+    int no_cch;   // env B200_NO_CCH: shortest paths by Gauss-Seidel sweeps / label correcting everywhere (A/B, parity tests)
     int last_launches;
     size_t smem_f32, smem_f64;
     int warps_f32, warps_f64;

@@ -190,6 +190,8 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
         (rc = upload(&g->out_eid, out_eid)))
         return rc;
     g->max_t0 = *std::max_element(vt0.begin(), vt0.end());
+    g->min_t0 = *std::min_element(vt0.begin(), vt0.end());
+    g->no_cch = getenv("B200_NO_CCH") != nullptr;
     g->max_cap0 = *std::max_element(vcap.begin(), vcap.end());
     g->origins_host = (int32_t *)malloc(sizeof(int32_t) * std::max(O, 1));
     std::copy(origins.begin(), origins.end(), g->origins_host);
@@ -238,7 +240,7 @@ extern "C" int b200_graph_origins(const b200_graph *g, int32_t *origins_host)
 
 extern "C" int b200_assign_launches(const b200_graph *g) { return g ? g->last_launches : 0; }
 
-extern "C" int b200_assign_last_config(const b200_graph *g, int32_t cfg[4])
+extern "C" int b200_assign_last_config(const b200_graph *g, int32_t cfg[8])
 {
     B200_REQUIRE(g && cfg, "null argument");
     const bool general = !(g->static_ok && !g->force_general && !g->force_small) && !(g->small_ok && !g->force_general);
@@ -246,6 +248,8 @@ extern "C" int b200_assign_last_config(const b200_graph *g, int32_t cfg[4])
     cfg[1] = general ? std::max(g->last_cluster, 1) : 1;
     cfg[2] = general ? g->warm_start : 0;
     cfg[3] = general ? g->last_warps : 0;
+    cfg[4] = g->last_cch;
+    cfg[5] = cfg[6] = cfg[7] = 0;
     return 0;
 }
 

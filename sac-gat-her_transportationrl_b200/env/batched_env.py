@@ -78,11 +78,12 @@ class AssignmentEngine:
 
     @property
     def last_config(self) -> Dict[str, int]:
-        """Launch configuration of the last ``assign`` (kernels, cluster size, warm start, warps per CTA)."""
+        """Launch configuration of the last ``assign`` (kernels, cluster size, warm start, warps per CTA,
+        contraction-hierarchy shortest paths)."""
         import ctypes as C
-        cfg = (C.c_int32 * 4)()
+        cfg = (C.c_int32 * 8)()
         _native.check(self.lib.b200_assign_last_config(self.h, cfg), "b200_assign_last_config")
-        return dict(launches=cfg[0], cluster=cfg[1], warm=cfg[2], warps=cfg[3])
+        return dict(launches=cfg[0], cluster=cfg[1], warm=cfg[2], warps=cfg[3], cch=cfg[4])
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

@@ -633,3 +633,48 @@ def test_sf_4096_flip_report(b200env, native_lib, sf_graph, golden, capsys):
     with capsys.disabled():
         print(f"\n[sf_4096_flip_report] {report}")
     assert report["fp32"]["flips"] <= 4 and report["fp64"]["flips"] <= 4
+
+
+# ---------------------------------------------------------------------------------------------
+# contraction-hierarchy shortest paths (exactly summable fp32 costs) vs label correcting
+# ---------------------------------------------------------------------------------------------
+def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, native_lib, sf_graph, sf_oracle, golden,
+                                                                       monkeypatch):
+    """The specialised kernel takes its distances from two sweeps over the customized contraction
+    hierarchy when every path sum is exact in fp64 (fp32 link state, host-checked); B200_NO_CCH forces
+    the Gauss-Seidel sweeps.  Both must give the same bits as each other and as the C oracle, for every
+    method, cold and warm start; fp64 link state and a cost range that breaks exactness must NOT take
+    the hierarchy."""
+    G = golden("sf_batch4096_fw_k20.npz")
+    masks = _masks_from_idx(G["dmg"][:512], 76)
+    cch = _engine(b200env, sf_graph, "fp32")
+    monkeypatch.setenv("B200_NO_CCH", "1")
+    gs = _engine(b200env, sf_graph, "fp32")
+    monkeypatch.delenv("B200_NO_CCH")
+    for method, K in (("fw", 20), ("msa", 20), ("cfw", 12), ("fw_ls", 8)):
+        a = _assign(cch, masks, K, method)
+        assert cch.last_config["cch"] == 1 and cch.kernel_name == "assign_static_kernel"
+        b = _assign(gs, masks, K, method)
+        assert gs.last_config["cch"] == 0
+        for key in ("flow", "tstt", "gap", "unassigned", "status"):
+            assert np.array_equal(a[key], b[key]), (method, key)
+        if method in ("fw", "msa"):
+            for s in range(0, 512, 32):
+                o = sf_oracle.assign(masks[s], None, K, method)
+                assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"], (method, s)
+        # warm start from the previous result, one link repaired
+        masks2 = masks.copy()
+        masks2[np.arange(512), G["dmg"][:512, 3]] = 0
+        a2 = _assign(cch, masks2, K, method, flow0=a["flow"])
+        b2 = _assign(gs, masks2, K, method, flow0=a["flow"])
+        assert np.array_equal(a2["flow"], b2["flow"]) and np.array_equal(a2["tstt"], b2["tstt"]), method
+    # undamaged network, free-flow ties everywhere (iteration 0 of a cold start)
+    z = np.zeros((2, 76), np.uint8)
+    assert np.array_equal(_assign(cch, z, 20, "fw")["flow"], _assign(gs, z, 20, "fw")["flow"])
+    # guards: double link state, and a BPR exponent whose clipped cost range is not exactly summable
+    f64 = _engine(b200env, sf_graph, "fp64")
+    _assign(f64, masks[:4], 5, "fw")
+    assert f64.last_config["cch"] == 0
+    steep = _engine(b200env, sf_graph, "fp32", bpr_beta=9.0)
+    out = _assign(steep, masks[:4], 5, "fw")
+    assert steep.last_config["cch"] == 0 and np.all(np.isfinite(out["tstt"]))
