@@ -34,7 +34,8 @@ extern "C" {
 typedef struct b200_graph b200_graph; /* opaque: static network resident in HBM */
 
 enum { B200_F32 = 0, B200_F64 = 1 };
-/* assignment_method (reference :55, :318-335); FW_LS = fw with bisection line search (extension) */
+/* assignment_method (reference :55, :318-335); FW_LS = fw with a bisection line search (extension;
+ * the first step is 1 like fw's 2/(it+2), later steps solve sum_e (aux_e - f_e) t_e(f + lam (aux - f)) = 0) */
 enum { B200_MSA = 0, B200_FW = 1, B200_CFW = 2, B200_FW_LS = 3 };
 enum { B200_EINVAL = -1, B200_ENOMEM = -2, B200_EUNSUPPORTED = -3 };
 /* bits of the per-scenario status word */

@@ -478,7 +478,8 @@ __device__ void cta_update(Cta<REAL> &c, const Params &p, const uint8_t *dmg_b, 
         else if (p.method == B200_FW) lam64 = 2.0 / (it + 2.0);
         else {
             // bisection on g(lam) = sum_e (aux_e - f_e) t_e(f + lam (aux - f)), fixed probe count
-            if (ls_derivative<REAL>(c, p, dmg_b, 1.0) <= 0.0) lam64 = 1.0;
+            // first step = the all-or-nothing load itself (as fw's 2/(it+2)): flow = 0 is not feasible
+            if (it == 0 || ls_derivative<REAL>(c, p, dmg_b, 1.0) <= 0.0) lam64 = 1.0;
             else {
                 double lo = 0.0, hi = 1.0;
                 for (int i = 0; i < p.ls_iters; ++i) {

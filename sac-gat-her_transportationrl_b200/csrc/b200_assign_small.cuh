@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(kSmallWarps * 32, B200_SMALL_MINB) assign_smal
                     });
                     return warp_sum_f64(g);
                 };
-                if (deriv(1.0) <= 0.0) lam64 = 1.0;
+                // first step = the all-or-nothing load itself (as fw's 2/(it+2)): flow = 0 is not feasible
+                if (it == 0 || deriv(1.0) <= 0.0) lam64 = 1.0;
                 else {
                     double lo = 0.0, hi = 1.0;
                     for (int i = 0; i < p.ls_iters; ++i) {

@@ -440,6 +440,7 @@ def test_line_search_beats_fixed_step_gap(b200env, native_lib, sf_graph, sf_orac
     ls = _assign(eng, masks, 30, "fw_ls")
     fw = _assign(eng, masks, 30, "fw")
     assert np.median(ls["gap"]) < np.median(fw["gap"])
+    assert np.all(ls["gap"] > -1e-9) and np.all(ls["tstt"] <= fw["tstt"] * 1.05)   # a real descent, not a collapse to zero flow
     for b in range(4):
         o = sf_oracle.assign(masks[b], None, 30, "fw_ls", dtype=np.float64)
         np.testing.assert_allclose(ls["flow"][b], o["flow"], rtol=1e-6, atol=1e-3)
