@@ -105,6 +105,15 @@ int b200_assign_launches(const b200_graph *g);
  * than from label correcting, cfg[5..7] reserved (0).  Parity tests use it to prove that the path
  * they mean to cover (cluster mode, warm start, hierarchy) is the one that ran. */
 int b200_assign_last_config(const b200_graph *g, int32_t cfg[8]);
+/* Host-only self-check of the contraction-hierarchy planner behind the general fused kernel
+ * (csrc/b200_cch.cu): plans the hierarchy of the link list, then replays on the CPU exactly the
+ * schedule the kernel executes (customization rows, up phase, down-sweep batches) for one cost
+ * vector (fp64 [E], link order) and one origin; dist_out fp64 [N] (+inf = unreachable) must equal
+ * scipy's Dijkstra distances bit for bit when the costs sum exactly (reference :485-489).
+ * stats: optional int64[8] = filled edges, lower triangles, down-region entries, up-region entries,
+ * distance slots, down batches, customization rows, 0.  Needs no GPU. */
+int b200_cch_host_sssp(int num_nodes, int num_links, const int32_t *row, const int32_t *col, const double *cost,
+                       int origin, double *dist_out, int64_t *stats);
 /* Which fused kernel b200_assign dispatches to for this network ("assign_static_kernel",
  * "assign_small_kernel" or "assign_fused_kernel"; static string). */
 const char *b200_assign_kernel_name(const b200_graph *g);

@@ -14,7 +14,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("B200_LIB", os.path.join(PKG_DIR, "libb200assign.so"))  # env override: kernel A/B runs
-SOURCES = ["b200_graph.cu", "b200_assign.cu", "b200_assign_small.cu", "b200_assign_static.cu", "b200_env.cu",
+SOURCES = ["b200_graph.cu", "b200_cch.cu", "b200_assign.cu", "b200_assign_small.cu", "b200_assign_static.cu", "b200_env.cu",
            "b200_gat.cu"]
 HEADERS = ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", "b200_assign_static.cuh", "b200_topo_siouxfalls.h",
            os.path.join("..", "..", "include", "b200_assign.h")]
@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
     "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
-    "b200_assign_launches", "b200_assign_last_config", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_assign_launches", "b200_assign_last_config", "b200_cch_host_sssp", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
     "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
 ]
 
@@ -72,6 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             "b200_assign_static.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_static.cuh",
                                       "b200_topo_siouxfalls.h", api],
             "b200_graph.cu": ["b200_common.cuh", api], "b200_env.cu": ["b200_common.cuh", api],
+            "b200_cch.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
             "b200_gat.cu": ["b200_common.cuh", api]}
     procs = []
     for src in SOURCES:
@@ -118,6 +119,7 @@ def _declare(lib) -> None:
     lib.b200_assign.argtypes = [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, _vp]
     lib.b200_assign_launches.argtypes = [_vp]
     lib.b200_assign_last_config.argtypes = [_vp, _vp]
+    lib.b200_cch_host_sssp.argtypes = [_i, _i, _vp, _vp, _vp, _i, _vp, _vp]
     lib.b200_assign_kernel_name.argtypes = [_vp]
     lib.b200_register_static_plugin.argtypes = [C.c_char_p]
     lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]

@@ -40,14 +40,29 @@ struct Cta {
     int N, E;
     bool intq;   // link loads are accumulated as int32 in the aux array (exact, order-independent)
     bool alias_cnt;   // pending-children counters live in the upper half of dist[] (see warp_offsets)
+    // contraction-hierarchy weights (b200_cch.cu): down region / up region, each either in shared memory
+    // or in this CTA's slice of the HBM workspace; position pos of the logical array is wd[pos] below
+    // cch_wd and wu[pos - cch_wd] from there on (the +inf and dummy slots follow the up region)
+    double *wd, *wu;
+    int cch_wd;
 
     // link load of link e as REAL, whatever the accumulation type
     __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
 
-    __device__ void carve(unsigned char *smem, const Params &p, int warps, int slots = 1)
+    __device__ void carve(unsigned char *smem, const Params &p, int warps, bool cch = false)
     {
         alias_cnt = (sizeof(REAL) == 4 ? p.alias32 : p.alias64) != 0;
-        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt, slots);
+        const int wmode = cch ? p.cch.wmode : 0;
+        const size_t w_smem = !cch ? 0 : (wmode == 2 ? (size_t)(p.cch.wd + p.cch.wu + 2) * 8 : wmode == 1 ? (size_t)p.cch.wd * 8 : 0);
+        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt, cch ? p.cch.slots : 0,
+                                   w_smem);
+        if (cch) {
+            double *ws_cta = p.cch.ws + (size_t)blockIdx.x * p.cch.ws_stride;
+            double *sm = (double *)(smem + L.off_cchw);
+            cch_wd = p.cch.wd;
+            wd = wmode >= 1 ? sm : ws_cta;
+            wu = wmode == 2 ? sm + p.cch.wd : (wmode == 1 ? ws_cta : ws_cta + p.cch.wd);
+        }
         bar = (uint64_t *)(smem + L.off_bar);
         topo = (uint16_t *)(smem + L.off_topo);
         in_ptr = topo;
@@ -66,6 +81,7 @@ struct Cta {
         E = p.E;
     }
     __device__ double *dist(int warp) const { return (double *)(warp_base + warp_stride * warp); }
+    __device__ __forceinline__ double *wpos(int pos) const { return pos < cch_wd ? wd + pos : wu + (pos - cch_wd); }
 
     // Stage the static topology into shared memory with one TMA bulk copy (UBLKCP).
     __device__ void stage_topology(const Params &p)
@@ -120,13 +136,11 @@ struct WarpScratch {
     uint32_t *cntw, *mask;
     int *tail;
 };
-// Scratch of origin slot `slot` of a warp (a warp works on 32 / G origins at once, see below).
 template <typename REAL>
-__device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp, int slot = 0, int slots = 1)
+__device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp, int dist_slots = 0)
 {
-    const WarpOffsets W = warp_offsets(c.N, c.alias_cnt);
-    unsigned char *base = c.warp_base + c.warp_stride * warp + W.total * slot;
-    (void)slots;
+    const WarpOffsets W = warp_offsets(c.N, c.alias_cnt, dist_slots);
+    unsigned char *base = c.warp_base + c.warp_stride * warp;
     WarpScratch s;
     s.dist = (double *)base;
     s.pk = (uint16_t *)(base + W.pk);
@@ -142,60 +156,42 @@ __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp
 // file header).  Work is driven by a frontier: a node is re-examined (pull over its in-links) only
 // after one of its in-neighbours improved; the "queued" bit of a node is cleared before its
 // in-neighbours are read, so an improvement that lands after the read re-queues the node for the
-// next round.  Rounds <= longest shortest path in hops.
-//
-// SUB-WARP GROUPS: a group of G lanes (G = 8, 16 or 32) owns one origin, so a warp advances 32 / G
-// origins in lock step.  On networks with narrow frontiers (a handful of nodes per round) a full
-// warp per origin wastes most lanes of every instruction, and the kernel is issue-bound once enough
-// warps are resident; with G = 8 the same instruction stream serves four origins.  All control flow
-// is warp-uniform (loops run while ANY group has work), group-local quantities are derived from
-// ballots masked with the group's lane mask.  `origin < 0` marks an idle group.
+// next round.  Rounds <= longest shortest path in hops.  One warp owns one origin.
 //
 // Warm start (tree != nullptr: this origin's tree of the previous iteration, in-link slot per node):
 // the old tree is re-evaluated top-down under the new costs - every label is then the length of a
 // real path, i.e. a valid upper bound - and ALL nodes are queued once, so the first round is a
 // full verification pass and later rounds only follow actual changes.  The fixed point, and with
 // it the result, is the same as from a cold start.
-// Queue tails live in a group-uniform register: new entries are placed by ballot + popcount, the
+// Queue tails live in a warp-uniform register: new entries are placed by ballot + popcount, the
 // only shared-memory atomics are the "already queued" bits.  Link loops are unrolled by kLinkUnroll
 // so the dependent shared-memory loads of one step are issued together.
-// `cond` is uniform within a group of G lanes; true if it holds in any group of the warp (with one
-// group per warp that is just `cond`: no vote needed)
-template <int G>
-__device__ __forceinline__ bool group_any(bool cond)
-{
-    if constexpr (G == 32) return cond;
-    else return __any_sync(0xffffffffu, cond);
-}
+template <typename REAL>
+__device__ void warp_select_pred(const Cta<REAL> &c, int origin, const WarpScratch &s);
 
-template <typename REAL, int G, int kLinkUnroll = 4>
+template <typename REAL, int kLinkUnroll = 4>
 __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, const uint16_t *tree = nullptr)
 {
-    const int lane = threadIdx.x & 31, gl = lane & (G - 1), N = c.N;
+    const int lane = threadIdx.x & 31, N = c.N;
     const unsigned FULL = 0xffffffffu;
-    const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane - gl));
-    const unsigned lt = ((1u << gl) - 1u) << (lane - gl);   // lower lanes of my group
-    const bool live = origin >= 0;
+    const unsigned lt = (1u << lane) - 1u;   // lower lanes
     double *dist = s.dist;
     const uint16_t *__restrict__ in_ptr = c.in_ptr, *__restrict__ in_src = c.in_src, *__restrict__ out_ptr = c.out_ptr,
                    *__restrict__ out_dst = c.out_dst;
     const double *__restrict__ w = c.w;
-    if (live)
-        for (int v = gl; v < N; v += G) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
+    for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     uint16_t *cur = s.q0, *nxt = s.q1;
     int count = 0;
     if (tree) {   // warp-uniform (the iteration index decides)
-        if (live) {
-            for (int v = gl; v < N; v += G) s.pk[v] = tree[v];
-            if (gl == 0) cur[0] = (uint16_t)origin;
-            count = 1;
-        }
+        for (int v = lane; v < N; v += 32) s.pk[v] = tree[v];
+        if (lane == 0) cur[0] = (uint16_t)origin;
+        count = 1;
         __syncwarp();
-        while (group_any<G>(count > 0)) {   // breadth-first over the old tree's children
+        while (count > 0) {   // breadth-first over the old tree's children
             int ntail = 0;
-            for (int base = 0; group_any<G>(base < count); base += G) {
-                const bool valid = base + gl < count;
-                const int u = valid ? (int)cur[base + gl] : 0;
+            for (int base = 0; base < count; base += 32) {
+                const bool valid = base + lane < count;
+                const int u = valid ? (int)cur[base + lane] : 0;
                 const double du = valid ? dist[u] : 0.0;
                 const int j0 = valid ? out_ptr[u] : 0, j1 = valid ? out_ptr[u + 1] : 0;
                 for (int jb = 0; __any_sync(FULL, j0 + jb < j1); jb += kLinkUnroll) {
@@ -208,7 +204,7 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                     for (int i = 0; i < kLinkUnroll; ++i) {
                         const bool child = ks[i] != kNoPk && in_src[ks[i]] == u;
                         if (child) dist[xs[i]] = du + w[ks[i]];
-                        const unsigned m = __ballot_sync(FULL, child) & gmask;
+                        const unsigned m = __ballot_sync(FULL, child);
                         if (child) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
                         ntail += __popc(m);
                     }
@@ -219,35 +215,30 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
             uint16_t *t = cur; cur = nxt; nxt = t;
         }
         // queue every node but the origin
-        if (live) {
-            for (int v = gl; v < N; v += G)
-                if (v != origin) cur[v - (v > origin ? 1 : 0)] = (uint16_t)v;
-            for (int i = gl; i < (N + 31) / 32; i += G) s.mask[i] = 0xffffffffu;
-            count = N - 1;
-        }
+        for (int v = lane; v < N; v += 32)
+            if (v != origin) cur[v - (v > origin ? 1 : 0)] = (uint16_t)v;
+        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0xffffffffu;
+        count = N - 1;
         __syncwarp();
-        if (live && gl == 0) atomicAnd(&s.mask[origin >> 5], ~(1u << (origin & 31)));
+        if (lane == 0) atomicAnd(&s.mask[origin >> 5], ~(1u << (origin & 31)));
     } else {
-        if (live)
-            for (int i = gl; i < (N + 31) / 32; i += G) s.mask[i] = 0u;
+        for (int i = lane; i < (N + 31) / 32; i += 32) s.mask[i] = 0u;
         __syncwarp();
-        if (live) {
-            const int o0 = out_ptr[origin];
-            count = out_ptr[origin + 1] - o0;
-            for (int j = gl; j < count; j += G) {
-                const int x = out_dst[o0 + j];
-                cur[j] = (uint16_t)x;
-                atomicOr(&s.mask[x >> 5], 1u << (x & 31));
-            }
+        const int o0 = out_ptr[origin];
+        count = out_ptr[origin + 1] - o0;
+        for (int j = lane; j < count; j += 32) {
+            const int x = out_dst[o0 + j];
+            cur[j] = (uint16_t)x;
+            atomicOr(&s.mask[x >> 5], 1u << (x & 31));
         }
     }
     __syncwarp();
     int rounds = 0, capped = 0;
-    while (group_any<G>(count > 0)) {
+    while (count > 0) {
         int ntail = 0;
-        for (int base = 0; group_any<G>(base < count); base += G) {
-            const bool valid = base + gl < count;
-            const int v = valid ? (int)cur[base + gl] : 0;
+        for (int base = 0; base < count; base += 32) {
+            const bool valid = base + lane < count;
+            const int v = valid ? (int)cur[base + lane] : 0;
             if (valid) atomicAnd(&s.mask[v >> 5], ~(1u << (v & 31)));
             __syncwarp();
             bool improved = false;
@@ -289,7 +280,7 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
                 }
 #pragma unroll
                 for (int i = 0; i < kLinkUnroll; ++i) {
-                    const unsigned m = __ballot_sync(FULL, fresh[i]) & gmask;
+                    const unsigned m = __ballot_sync(FULL, fresh[i]);
                     if (fresh[i]) nxt[ntail + __popc(m & lt)] = (uint16_t)xs[i];
                     ntail += __popc(m);
                 }
@@ -300,91 +291,210 @@ __device__ int warp_sssp(const Cta<REAL> &c, int origin, const WarpScratch &s, c
         uint16_t *t = cur; cur = nxt; nxt = t;
         if (++rounds > N + 1) { capped = count > 0; break; }
     }
-    // predecessor: tight in-link with the smallest dist[u], then the largest u
-    if (live) {
-        for (int v = gl; v < N; v += G) {
-            const double dv = dist[v];
-            int bk = kNoPk, bu = -1;
-            double bdu = B200_INF_F64;
-            if (v != origin && dv < B200_INF_F64) {
-                const int k1 = in_ptr[v + 1];
-                for (int k = in_ptr[v]; k < k1; ++k) {
-                    const int u = in_src[k];
-                    const double du = dist[u];
-                    if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
-                        bk = k; bu = u; bdu = du;
-                    }
+    warp_select_pred<REAL>(c, origin, s);
+    return capped;
+}
+
+// predecessor: tight in-link with the smallest dist[u], then the largest u (scipy's rule, SURVEY.md
+// Appendix A.1; in-links of a node are stored by ascending tail id)
+template <typename REAL>
+__device__ void warp_select_pred(const Cta<REAL> &c, int origin, const WarpScratch &s)
+{
+    const int lane = threadIdx.x & 31, N = c.N;
+    const double *dist = s.dist;
+    const uint16_t *__restrict__ in_ptr = c.in_ptr, *__restrict__ in_src = c.in_src;
+    const double *__restrict__ w = c.w;
+    for (int v = lane; v < N; v += 32) {
+        const double dv = dist[v];
+        int bk = kNoPk, bu = -1;
+        double bdu = B200_INF_F64;
+        if (v != origin && dv < B200_INF_F64) {
+            const int k1 = in_ptr[v + 1];
+            for (int k = in_ptr[v]; k < k1; ++k) {
+                const int u = in_src[k];
+                const double du = dist[u];
+                if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
+                    bk = k; bu = u; bdu = du;
                 }
             }
-            s.pk[v] = (uint16_t)bk;
         }
+        s.pk[v] = (uint16_t)bk;
     }
     __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// S2 through the customizable contraction hierarchy (tables: b200_cch.cu)
+// ---------------------------------------------------------------------------------------------
+// Customization, once per (scenario, iteration), all warps of the CTA: every filled edge starts from
+// its own link cost (+inf for a pure shortcut), then the rows of each level - 32 edges with their
+// lower triangles, most triangles first - are dealt to the warps round-robin; a CTA barrier separates
+// the levels (the two lower edges of a triangle are final one level earlier).
+template <typename REAL>
+__device__ void cta_customize(const Cta<REAL> &c, const Params &p)
+{
+    const CchParams &h = p.cch;
+    for (int e = threadIdx.x; e < h.F; e += blockDim.x) {
+        const uint32_t wi = __ldg(h.cz_init + e);
+        const int slot = (int)(wi >> 16);
+        *c.wpos((int)(wi & 0xffffu)) = slot == 0xffff ? B200_INF_F64 : c.w[slot];
+    }
+    const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int off = 0, turn = 0;
+    for (int r = 0; r < h.cz_rows; ++r) {
+        const uint32_t desc = __ldg(h.cz_desc + r);
+        const int T = (int)(desc & 0xffffu);
+        if (desc & 0x10000u) { __syncthreads(); turn = 0; }
+        if (turn == warp) {
+            const uint32_t *row = h.cz_tab + off;
+            double *dst = c.wpos((int)__ldg(row + lane));
+            double acc = *dst;
+            for (int t = 0; t < T; ++t) {
+                const uint32_t tri = __ldg(row + 32 * (t + 1) + lane);
+                const double cand = *c.wpos((int)(tri & 0xffffu)) + *c.wpos((int)(tri >> 16));
+                acc = cand < acc ? cand : acc;
+            }
+            *dst = acc;
+        }
+        off += 32 * (T + 1);
+        turn = turn + 1 == W ? 0 : turn + 1;
+    }
+    __syncthreads();
+}
+
+// Bellman-Ford to the least fixed point with nothing but dist[]: the fallback for an origin whose
+// labels leave the exactly-summable range (never on the shipped networks; B200_CCH_LIMIT forces it
+// in the tests).
+template <typename REAL>
+__device__ int warp_sssp_bf(const Cta<REAL> &c, int origin, const WarpScratch &s)
+{
+    const int lane = threadIdx.x & 31, N = c.N;
+    double *dist = s.dist;
+    for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
+    __syncwarp();
+    for (int round = 0; round <= N; ++round) {
+        bool changed = false;
+        for (int v = lane; v < N; v += 32) {
+            const double dv = dist[v];
+            double best = dv;
+            for (int k = c.in_ptr[v]; k < c.in_ptr[v + 1]; ++k) {
+                const double cand = dist[c.in_src[k]] + c.w[k];
+                best = cand < best ? cand : best;
+            }
+            if (best < dv) { dist[v] = best; changed = true; }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, changed)) return 0;
+    }
+    return 1;
+}
+
+// One warp, one origin: up phase along the elimination-tree ancestors of the origin, then the static
+// down sweep over the ELL batches (see b200_cch.cu); labels are exact sums, checked below.
+template <typename REAL>
+__device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int origin, const WarpScratch &s)
+{
+    const CchParams &h = p.cch;
+    const int lane = threadIdx.x & 31, N = c.N;
+    double *dist = s.dist;
+    for (int v = lane; v < h.slots; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
+    __syncwarp();
+    const double *__restrict__ wu = c.wu;
+    for (int a = origin; a < N; a = __ldg(h.parent + a)) {
+        const double da = dist[a];   // final: every lower ancestor has pushed already
+        if (da < B200_INF_F64) {
+            const int j1 = __ldg(h.uo_ptr + a + 1);
+            for (int j = __ldg(h.uo_ptr + a) + lane; j < j1; j += 32) {
+                const int x = __ldg(h.uo_head + j);
+                const double cand = da + wu[j];
+                if (cand < dist[x]) dist[x] = cand;
+            }
+        }
+        __syncwarp();
+    }
+    const double *__restrict__ wd = c.wd;
+    const uint16_t *__restrict__ tails = h.dn_tail;
+    int off = lane;
+    for (int b = 0; b < h.dn_batches; ++b) {
+        const uint32_t desc = __ldg(h.dn_desc + b);
+        const int deg = (int)(desc & 0xffffu);
+        if (desc & 0x10000u) __syncwarp();   // next level: the labels it pulls from are complete
+        const int dest = __ldg(h.dn_node + b * 32 + lane);
+        double best = dist[dest];
+#pragma unroll 4
+        for (int j = 0; j < deg; ++j) {
+            const double cand = dist[__ldg(tails + off + j * 32)] + wd[off + j * 32];
+            best = cand < best ? cand : best;
+        }
+        dist[dest] = best;
+        off += deg * 32;
+    }
+    __syncwarp();
+    unsigned mx = 0;
+    for (int v = lane; v < N; v += 32) {
+        const unsigned hi = (unsigned)__double2hiint(dist[v]);
+        mx = hi < 0x7ff00000u && hi > mx ? hi : mx;
+    }
+    int capped = 0;
+    if (__reduce_max_sync(0xffffffffu, mx) >= h.exact_hi) capped = warp_sssp_bf<REAL>(c, origin, s);
+    warp_select_pred<REAL>(c, origin, s);
     return capped;
 }
 
 // ---------------------------------------------------------------------------------------------
-// S3: one group of lanes, one origin - subtree demand sums, leaves first (Kahn), link loads into c.aux
+// S3: one warp, one origin - subtree demand sums, leaves first (Kahn), link loads into c.aux
 // ---------------------------------------------------------------------------------------------
 // Every tree link is handled once: a node whose children are all done adds its subtree sum to
 // its in-link and to its parent.  The frontier of "ready" nodes is a queue; pending-children
 // counters are 16-bit, two per 32-bit word, updated with 32-bit shared-memory atomics.
 // INTQ: sums are int32 (exact, order-independent); otherwise REAL atomics (order-dependent in the
 // last bits, like any parallel sum).  Returns this lane's share of the unassigned demand.
-template <typename REAL, bool INTQ, int G>
+template <typename REAL, bool INTQ>
 __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
     using QT = typename std::conditional<INTQ, int, REAL>::type;
-    const int lane = threadIdx.x & 31, gl = lane & (G - 1), N = c.N;
+    const int lane = threadIdx.x & 31, N = c.N;
     const unsigned FULL = 0xffffffffu;
-    const unsigned gmask = G == 32 ? FULL : (((1u << (G & 31)) - 1u) << (lane - gl));
-    const unsigned lt = ((1u << gl) - 1u) << (lane - gl);
-    const bool live = origin >= 0;
+    const unsigned lt = (1u << lane) - 1u;
     const uint16_t *__restrict__ in_src = c.in_src, *__restrict__ in_eid = c.in_eid;
     QT *sacc = (QT *)s.dist;   // dist is dead once pk is chosen
     QT *auxq = (QT *)c.aux;
     const REAL *q = (const REAL *)p.od_q;
-    if (live) {
-        for (int v = gl; v < N; v += G) sacc[v] = 0;
-        for (int i = gl; i < (N + 1) / 2; i += G) s.cntw[i] = 0u;
-    }
+    for (int v = lane; v < N; v += 32) sacc[v] = 0;
+    for (int i = lane; i < (N + 1) / 2; i += 32) s.cntw[i] = 0u;
     __syncwarp();
-    if (live) {
-        const int jd1 = __ldg(p.od_ptr + slot + 1);
-        for (int j = __ldg(p.od_ptr + slot) + gl; j < jd1; j += G) sacc[__ldg(p.od_dst + j)] = (QT)q[j];
-    }
+    const int jd1 = __ldg(p.od_ptr + slot + 1);
+    for (int j = __ldg(p.od_ptr + slot) + lane; j < jd1; j += 32) sacc[__ldg(p.od_dst + j)] = (QT)q[j];
     __syncwarp();
     double un = 0.0;
-    if (live) {
-        for (int v = gl; v < N; v += G) {
-            const int k = s.pk[v];
-            if (k != kNoPk) {
-                const int u = in_src[k];
-                atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
-            } else {
-                un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
-            }
+    for (int v = lane; v < N; v += 32) {
+        const int k = s.pk[v];
+        if (k != kNoPk) {
+            const int u = in_src[k];
+            atomicAdd(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
+        } else {
+            un += (double)sacc[v];   // unreachable destination, or demand to the origin itself (reference :496)
         }
     }
     __syncwarp();
     uint16_t *cur = s.q0, *nxt = s.q1;
     int count = 0;
-    for (int v0 = 0; v0 < N; v0 += G) {
-        const int v = v0 + gl;
+    for (int v0 = 0; v0 < N; v0 += 32) {
+        const int v = v0 + lane;
         bool leaf = false;
-        if (live && v < N && s.pk[v] != kNoPk) leaf = ((s.cntw[v >> 1] >> ((v & 1) * 16)) & 0xffffu) == 0u;
-        const unsigned m = __ballot_sync(FULL, leaf) & gmask;
+        if (v < N && s.pk[v] != kNoPk) leaf = ((s.cntw[v >> 1] >> ((v & 1) * 16)) & 0xffffu) == 0u;
+        const unsigned m = __ballot_sync(FULL, leaf);
         if (leaf) cur[count + __popc(m & lt)] = (uint16_t)v;
         count += __popc(m);
     }
     __syncwarp();
-    while (group_any<G>(count > 0)) {
+    while (count > 0) {
         int ntail = 0;
-        for (int base = 0; group_any<G>(base < count); base += G) {
+        for (int base = 0; base < count; base += 32) {
             bool ready = false;
             int u = 0;
-            if (base + gl < count) {
-                const int v = cur[base + gl], k = s.pk[v];
+            if (base + lane < count) {
+                const int v = cur[base + lane], k = s.pk[v];
                 u = in_src[k];
                 const QT sv = sacc[v];
                 if (sv != (QT)0) {
@@ -394,7 +504,7 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
                 const uint32_t old = atomicSub(&s.cntw[u >> 1], (u & 1) ? 0x10000u : 1u);
                 ready = ((old >> ((u & 1) * 16)) & 0xffffu) == 1u && u != origin;   // that was the last child
             }
-            const unsigned m = __ballot_sync(FULL, ready) & gmask;
+            const unsigned m = __ballot_sync(FULL, ready);
             if (ready) nxt[ntail + __popc(m & lt)] = (uint16_t)u;
             ntail += __popc(m);
         }
@@ -405,10 +515,10 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
     return un;
 }
 
-template <typename REAL, int G>
+template <typename REAL>
 __device__ __forceinline__ double warp_aon(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
-    return c.intq ? warp_aon_peel<REAL, true, G>(c, p, slot, origin, s) : warp_aon_peel<REAL, false, G>(c, p, slot, origin, s);
+    return c.intq ? warp_aon_peel<REAL, true>(c, p, slot, origin, s) : warp_aon_peel<REAL, false>(c, p, slot, origin, s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -589,7 +699,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) sssp_kernel(Params p)
         for (int s = warp; s < p.O; s += W) {
             const int o = __ldg(p.origins + s);
             const WarpScratch ws = warp_scratch(c, warp);
-            capped |= warp_sssp<REAL, 32>(c, o, ws);
+            capped |= warp_sssp<REAL>(c, o, ws);
             const size_t base = ((size_t)b * p.O + s) * p.N;
             for (int v = lane; v < p.N; v += 32) {
                 const int k = ws.pk[v];
@@ -626,7 +736,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32) aon_kernel(Params p)
             const int32_t *pe = p.pedge_in + ((size_t)b * p.O + s) * p.N;
             for (int v = lane; v < p.N; v += 32) { const int e = pe[v]; ws.pk[v] = (uint16_t)(e < 0 ? kNoPk : slot_of[e]); }
             __syncwarp();
-            un += warp_aon<REAL, 32>(c, p, s, o, ws);
+            un += warp_aon<REAL>(c, p, s, o, ws);
             __syncwarp();
         }
         un = warp_sum_f64(un);
@@ -729,7 +839,7 @@ __device__ void cluster_combine(Cta<REAL> &c, cg::cluster_group &cluster, double
 // MINB = 2: at most 64 registers per thread, for networks small enough that several CTAs share an
 // SM (occupancy is what this latency-bound kernel lives on); MINB = 1: up to 128 registers when
 // shared memory allows only one CTA per SM anyway (Chicago-Sketch-size)
-template <typename REAL, int MINB, int G, int U>
+template <typename REAL, int MINB, bool CCH>
 __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Params p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -737,10 +847,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int OPW = 32 / G;          // origins per warp
-    const int group = lane / G, gl = lane & (G - 1);
-    c.carve(smem, p, W, OPW);
+    c.carve(smem, p, W, CCH);
     c.stage_topology(p);
+    if (CCH) {
+        // zero weights of the ELL padding / partial-combine entries (never touched again), the +inf slot
+        for (int i = threadIdx.x; i < p.cch.wd; i += blockDim.x) c.wd[i] = 0.0;
+        if (threadIdx.x == 0) *c.wpos(p.cch.wd + p.cch.wu) = B200_INF_F64;
+    }
     double *un_s = &c.red[kMaxWarps * 2];
     int *flag_s = (int *)&c.red[kMaxWarps * 2 + 1];
     const int cluster_id = blockIdx.x / C, num_clusters = gridDim.x / C;
@@ -759,17 +872,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
             for (int e = threadIdx.x; e < c.E; e += blockDim.x) c.aux[e] = 0;
             if (threadIdx.x == 0) *un_s = 0.0;
             __syncthreads();   // (neighbours finished pulling last iteration's loads before its last cluster barrier)
+            if (CCH) cta_customize<REAL>(c, p);
             double un = 0.0;
             int capped = 0;
-            for (int s0 = (rank * W + warp) * OPW; s0 < p.O; s0 += C * W * OPW) {
-                const int s = s0 + group;                     // this lane group's origin slot
-                const int o = s < p.O ? __ldg(p.origins + s) : -1;
-                const WarpScratch ws = warp_scratch(c, warp, group, OPW);
-                uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + (s < p.O ? s : 0)) * p.N;
-                capped |= warp_sssp<REAL, G, U>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
-                if (o >= 0 && p.warm)
-                    for (int v = gl; v < p.N; v += G) tree[v] = ws.pk[v];   // next iteration's warm start
-                un += warp_aon<REAL, G>(c, p, s, o, ws);
+            for (int s = rank * W + warp; s < p.O; s += C * W) {
+                const int o = __ldg(p.origins + s);
+                const WarpScratch ws = warp_scratch(c, warp, CCH ? p.cch.slots : 0);
+                if (CCH) {
+                    capped |= warp_sssp_cch<REAL>(c, p, o, ws);
+                } else {
+                    uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + s) * p.N;
+                    capped |= warp_sssp<REAL>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
+                    if (p.warm)
+                        for (int v = lane; v < p.N; v += 32) tree[v] = ws.pk[v];   // next iteration's warm start
+                }
+                un += warp_aon<REAL>(c, p, s, o, ws);
                 __syncwarp();
             }
             un = warp_sum_f64(un);
@@ -827,16 +944,27 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.small_eid = g->small_eid; p.small_wpos = g->small_wpos;
     p.st_origpos = g->st_origpos;
     p.total_demand = g->total_demand;
+    if (g->cch_ok) {
+        p.cch.dn_desc = g->cch_dn_desc; p.cch.cz_init = g->cch_cz_init; p.cch.cz_desc = g->cch_cz_desc;
+        p.cch.cz_tab = g->cch_cz_tab; p.cch.dn_node = g->cch_dn_node; p.cch.dn_tail = g->cch_dn_tail;
+        p.cch.uo_ptr = g->cch_uo_ptr; p.cch.uo_head = g->cch_uo_head; p.cch.parent = g->cch_parent;
+        p.cch.F = g->cch_F; p.cch.wd = g->cch_wd; p.cch.wu = g->cch_wu; p.cch.slots = g->cch_slots;
+        p.cch.dn_batches = g->cch_dn_batches; p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
+        union { double d; unsigned long long u; } lim;
+        lim.d = g->cch_exact_limit;
+        p.cch.exact_hi = (unsigned)(lim.u >> 32);
+    }
     p.B = B; p.alpha = alpha; p.beta = beta;
     return p;
 }
 
 template <typename K>
-int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_in, cudaStream_t st, bool fused = false)
+int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_in, cudaStream_t st, bool fused = false,
+                      bool cch = false)
 {
     Params p = p_in;
-    const int warps = prec == B200_F32 ? g->warps_f32 : g->warps_f64;
-    const size_t smem = prec == B200_F32 ? g->smem_f32 : g->smem_f64;
+    const int warps = cch ? g->warps_cch : (prec == B200_F32 ? g->warps_f32 : g->warps_f64);
+    const size_t smem = cch ? g->smem_cch : (prec == B200_F32 ? g->smem_f32 : g->smem_f64);
     B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
@@ -852,7 +980,7 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
         // CTA per scenario (its direction scratch lives in the caller's [B][E] array).
         if (g->cluster_limit != 1 && p.method != B200_CFW) {
             const int want = std::min({8, g->cluster_limit > 0 ? g->cluster_limit : 8, capacity / std::max(p.B, 1),
-                                       (g->O + warps * std::max(p.slots, 1) - 1) / (warps * std::max(p.slots, 1))});
+                                       (g->O + warps - 1) / warps});
             while (cluster * 2 <= want) cluster *= 2;
         }
         if (cluster > 1) {
@@ -875,8 +1003,20 @@ int launch_cta_kernel(K kernel, const b200_graph *g, int prec, const Params &p_i
         if (cluster == 1) grid = (g->topo16_bytes <= 5120) ? p.B : std::min(p.B, capacity);
         // previous-iteration trees of the resident scenarios (the only allocation the library ever
         // makes after graph upload; it grows monotonically and is reused by later calls)
-        const size_t need = (size_t)(grid / cluster) * g->O * g->N * sizeof(uint16_t);
+        const size_t need = cch ? 0 : (size_t)(grid / cluster) * g->O * g->N * sizeof(uint16_t);
         b200_graph *gm = const_cast<b200_graph *>(g);
+        if (cch) {
+            // the part of the hierarchy weights that lives outside shared memory: one slice per CTA
+            const int wtot = g->cch_wd + g->cch_wu + 2;
+            p.cch.ws_stride = g->cch_wmode == 2 ? 0 : (g->cch_wmode == 1 ? g->cch_wu + 2 : wtot);
+            const size_t wneed = (size_t)grid * p.cch.ws_stride * sizeof(double);
+            if (wneed > gm->cch_ws_bytes) {
+                if (gm->cch_ws) { B200_CUDA(cudaStreamSynchronize(st)); B200_CUDA(cudaFree(gm->cch_ws)); gm->cch_ws = nullptr; gm->cch_ws_bytes = 0; }
+                B200_CUDA(cudaMalloc((void **)&gm->cch_ws, wneed));
+                gm->cch_ws_bytes = wneed;
+            }
+            p.cch.ws = gm->cch_ws;
+        }
         if (need > gm->tree_ws_bytes) {
             if (gm->tree_ws) { B200_CUDA(cudaStreamSynchronize(st)); B200_CUDA(cudaFree(gm->tree_ws)); gm->tree_ws = nullptr; gm->tree_ws_bytes = 0; }
             B200_CUDA(cudaMalloc((void **)&gm->tree_ws, need));
@@ -920,19 +1060,53 @@ int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out)
     // divide among the warps.  Ties go to fewer warps per CTA (more CTAs = more scenarios in flight).
     double best_score = -1.0;
     const int forced = getenv("B200_WARPS") ? atoi(getenv("B200_WARPS")) : 0;   // tuning experiments
-    const int slots = 32 / std::max(g->group_lanes, 8);   // origins per warp of the FUSED kernel
     for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-        SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, rb, gen_alias_host(g, rb), slots);
+        SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, rb, gen_alias_host(g, rb));
         if (L.total > kSmemLimit) break;
         if (forced && w != forced) continue;
-        const int O = std::max(g->O, 1), batch = w * slots;
+        const int O = std::max(g->O, 1), batch = w;
         const double eff = (double)O / (double)(((O + batch - 1) / batch) * batch);
         const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
         const double score = eff * batch * std::max(ctas, 1);
         if (score > best_score + 1e-9) { best_score = score; best = w; }
     }
-    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo16_bytes, best, rb, gen_alias_host(g, rb), slots).total;
+    if (best > 0 && smem_out) *smem_out = make_layout(g->N, g->E, g->topo16_bytes, best, rb, gen_alias_host(g, rb)).total;
     return best;
+}
+
+// Contraction-hierarchy variant of the fused kernel (fp32 link state): where the weights live and how
+// many warps a CTA gets.  Small hierarchies keep all of W in shared memory; otherwise the down region
+// (read in full by every origin) stays there if it leaves room for enough warps, and the rest - or all
+// of it - is served from the CTA's slice of the HBM workspace through L1/L2.  B200_CCH_W=0/1/2 forces
+// a placement (measurements).
+int b200_pick_warps_cch(b200_graph *g)
+{
+    if (!g->cch_ok) return -1;
+    const int forced_w = getenv("B200_WARPS") ? atoi(getenv("B200_WARPS")) : 0;
+    const int forced_m = getenv("B200_CCH_W") ? atoi(getenv("B200_CCH_W")) : -1;
+    double best_score = -1.0;
+    int best_w = -1, best_m = 0;
+    size_t best_smem = 0;
+    for (int mode = 2; mode >= 0; --mode) {
+        if (forced_m >= 0 && mode != forced_m) continue;
+        const size_t wb = mode == 2 ? (size_t)(g->cch_wd + g->cch_wu + 2) * 8 : mode == 1 ? (size_t)g->cch_wd * 8 : 0;
+        for (int w = kMinWarps; w <= kMaxWarps; ++w) {
+            SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, 4, true, g->cch_slots, wb);
+            if (L.total > kSmemLimit) break;
+            if (forced_w && w != forced_w) continue;
+            const int O = std::max(g->O, 1);
+            const double eff = (double)O / (double)(((O + w - 1) / w) * w);
+            const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
+            // resident warps, with a premium for weights in shared memory (every origin streams the down region)
+            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 1.25 : mode == 1 ? 1.15 : 1.0);
+            if (score > best_score + 1e-9) { best_score = score; best_w = w; best_m = mode; best_smem = L.total; }
+        }
+    }
+    if (best_w < 0) return -1;
+    g->warps_cch = best_w;
+    g->cch_wmode = best_m;
+    g->smem_cch = best_smem;
+    return best_w;
 }
 
 #define B200_PREC_OK(prec) B200_REQUIRE((prec) == B200_F32 || (prec) == B200_F64, "prec must be B200_F32 or B200_F64")
@@ -1030,13 +1204,20 @@ extern "C" int b200_assign(const b200_graph *g, int B, int prec, int K, int meth
         const size_t smem = prec == B200_F32 ? g->smem_f32 : g->smem_f64;
         const bool one_cta = 2 * (smem + 1024) > 228 * 1024;   // shared memory admits a single CTA per SM
         cudaStream_t st = (cudaStream_t)stream;
-        p.slots = 32 / g->group_lanes;
-#define B200_LAUNCH_FUSED(REAL, G, U)                                                           \
-    (one_cta ? launch_cta_kernel(assign_fused_kernel<REAL, 1, G, U>, g, prec, p, st, true)       \
-             : launch_cta_kernel(assign_fused_kernel<REAL, 2, G, U>, g, prec, p, st, true))
-        // G: see group_lanes.  U = 2 was measured on the Anaheim-size network (2.2 links/node): 6 % slower
-        // than 4 (more loop trips and votes), so the link loops stay 4-wide everywhere.
-        rc = prec == B200_F32 ? B200_LAUNCH_FUSED(float, 32, 4) : B200_LAUNCH_FUSED(double, 32, 4);
+        // fp32 link costs (>= t0 when alpha, beta >= 0) sum exactly in fp64 below the bound the kernel
+        // checks per origin: shortest paths from the contraction hierarchy instead of label correcting
+        const bool cch = prec == B200_F32 && g->cch_ok && !g->no_cch && g->warps_cch > 0 && alpha >= 0.0 && beta >= 0.0;
+        if (cch) {
+            const bool one_cta_c = 2 * (g->smem_cch + 1024) > 228 * 1024;
+            const_cast<b200_graph *>(g)->last_cch = 1;
+            rc = one_cta_c ? launch_cta_kernel(assign_fused_kernel<float, 1, true>, g, prec, p, st, true, true)
+                           : launch_cta_kernel(assign_fused_kernel<float, 2, true>, g, prec, p, st, true, true);
+        } else {
+#define B200_LAUNCH_FUSED(REAL)                                                                 \
+    (one_cta ? launch_cta_kernel(assign_fused_kernel<REAL, 1, false>, g, prec, p, st, true)      \
+             : launch_cta_kernel(assign_fused_kernel<REAL, 2, false>, g, prec, p, st, true))
+            rc = prec == B200_F32 ? B200_LAUNCH_FUSED(float) : B200_LAUNCH_FUSED(double);
+        }
 #undef B200_LAUNCH_FUSED
     }
     if (rc == 0) const_cast<b200_graph *>(g)->last_launches = 1;

@@ -29,10 +29,13 @@ struct WarpOffsets {
 };
 // alias_cnt: the subtree sums are 4-byte (int32 or float), so they fill only the lower half of the
 // dead dist[] array and the pending-children counters go into the upper half
-__host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt)
+// dist_slots: the contraction-hierarchy sweeps keep N labels, the +inf slot and the partial slots of split
+// destinations in the distance array (0 = N, the label-correcting kernel)
+__host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt, int dist_slots = 0)
 {
     WarpOffsets W;
-    const size_t dist_bytes = align16((size_t)N * 8), cnt_bytes = align16((size_t)((N + 1) / 2) * 4);
+    const size_t dist_bytes = align16((size_t)(dist_slots > N ? dist_slots : N) * 8),
+                 cnt_bytes = align16((size_t)((N + 1) / 2) * 4);
     size_t o = dist_bytes;
     W.pk = o;   o += align16((size_t)N * 2);
     W.q0 = o;   o += align16((size_t)N * 2);
@@ -46,11 +49,12 @@ __host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt)
 }
 
 struct SmemLayout {
-    size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_warp, warp_stride, total;
+    size_t off_bar, off_topo, off_w, off_aux, off_flow, off_red, off_cchw, off_warp, warp_stride, total;
 };
 
+// cch_w_bytes: contraction-hierarchy weights kept in shared memory (0 = none / label-correcting kernel)
 __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, int warps, int real_bytes, bool alias_cnt,
-                                                  int slots = 1)
+                                                  int dist_slots = 0, size_t cch_w_bytes = 0)
 {
     SmemLayout L;
     size_t o = 0;
@@ -60,8 +64,9 @@ __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, 
     L.off_aux = o;  o += align16((size_t)E * real_bytes);
     L.off_flow = o; o += align16((size_t)E * real_bytes);
     L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
+    L.off_cchw = o; o += align16(cch_w_bytes);
     L.off_warp = o;
-    L.warp_stride = warp_offsets(N, alias_cnt).total * slots;   // slots = origins a warp works on at once
+    L.warp_stride = warp_offsets(N, alias_cnt, dist_slots).total;
     L.total = o + L.warp_stride * warps;
     return L;
 }
@@ -72,14 +77,25 @@ struct SmallOffsets {
         warp_stride;
 };
 
+// contraction-hierarchy tables of the general fused kernel (b200_cch.cu), device pointers
+struct CchParams {
+    const uint32_t *dn_desc, *cz_init, *cz_desc, *cz_tab;
+    const uint16_t *dn_node, *dn_tail, *uo_ptr, *uo_head, *parent;
+    double *ws;            // per-CTA weight workspace in HBM (the part of W outside shared memory)
+    int F, wd, wu, slots, dn_batches, cz_rows;
+    int wmode;             // 0: W in HBM/L2, 1: down region in shared memory, 2: all of W in shared memory
+    int ws_stride;         // doubles per CTA in ws
+    unsigned exact_hi;     // high word of the exactness bound (labels >= it trigger the Bellman-Ford fallback)
+};
+
 struct Params {
     SmallOffsets so;
+    CchParams cch;
     // static network
     int N, E, O, topo_ints, off_in_src, off_in_eid;
     // general kernels: 16-bit topology blob, offsets in uint16 elements
     const uint16_t *topo16;
     int topo16_bytes, o16_in_src, o16_in_eid, o16_out_ptr, o16_out_dst;
-    int slots;  // general fused kernel: origins per warp (32 / lanes per origin group)
     int alias32, alias64;  // general kernel: counters aliased into dist[] (per precision; see warp_offsets)
     int warm;  // general kernel: warm-start shortest paths from the previous iteration's trees
     int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads

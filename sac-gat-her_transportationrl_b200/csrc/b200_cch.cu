@@ -1,0 +1,436 @@
+// Customizable contraction hierarchy (CCH) of the static network, planned once at graph upload
+// for the general fused assignment kernel (b200_assign.cu).
+//
+// Why: the reference runs scipy's Dijkstra from every origin in every iteration of every scenario
+// (src/env/repair_env.py:481-489).  The topology never changes - only the link costs do - so the
+// search order can be fixed ahead of time: eliminate the nodes in a nested-dissection-like order,
+// adding a shortcut (u,x) for every pair of remaining in-/out-neighbours of the eliminated node
+// ("lower triangle" (u,v),(v,x)).  Per (scenario, iteration) the CTA first CUSTOMIZES the weights
+// of the filled edges, W(u,x) = min(cost(u,x), min over lower triangles W(u,v) + W(v,x)); then the
+// distances from one origin are
+//   up phase    walk the origin's ancestors in the elimination tree, relax their edges to
+//               higher-ranked heads (a few dozen nodes), and
+//   down sweep  ONE pass over all nodes by decreasing rank, each pulling from its higher-ranked
+//               in-neighbours - a static schedule: nodes of one level are independent, their in-edges
+//               are stored as ELL rows (32 destinations x degree) in exactly the order the sweep reads.
+// Every filled edge is relaxed once per origin (Anaheim-size: 1 272 for 914 links; Chicago-Sketch-size:
+// 10 224 for 2 950) instead of the ~7 relaxations per link of frontier label correcting.
+//
+// Exactness: link costs are fp32 values >= min t0, so every path sum below 2^(q+52),
+// q = floor(log2(min t0)) - 23, is exact in fp64 and therefore independent of the association order:
+// the labels are bit for bit the ones Dijkstra (and the label-correcting kernel) produce, and the
+// tie rule picks the same predecessors.  The kernel checks the bound per origin and falls back to
+// Bellman-Ford on the rare origin that violates it (b200_assign.cu: warp_sssp_cch).
+//
+// Narrow levels of the down sweep split their high-degree destinations: chunks of in-edges go to
+// "partial" distance slots first, the node then combines its partials through zero-weight entries;
+// the chunk size is chosen per level by an instruction-count model of the sweep (down_layout).
+#include "b200_assign_internal.cuh"
+
+#include <map>
+#include <numeric>
+#include <set>
+#include <unordered_map>
+
+using namespace b200i;
+
+namespace {
+
+struct Plan {
+    int N = 0, F = 0;
+    std::vector<int> rank, order, parent;
+    std::vector<std::pair<int, int>> edges;                 // filled directed edges (tail, head)
+    std::vector<int> orig_slot;                             // CSC slot of the original link or -1
+    std::vector<std::vector<std::pair<int, int>>> tris;     // per edge: (edge (u,v), edge (v,x))
+};
+
+inline uint64_t key(int u, int x) { return ((uint64_t)(uint32_t)u << 32) | (uint32_t)x; }
+
+// Elimination in rounds of independent low-degree nodes (degree <= max(min degree, 2)): keeps the
+// elimination tree shallow, which is what bounds the number of levels of the down sweep.
+Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
+{
+    Plan P;
+    P.N = N;
+    std::vector<std::set<int>> out(N), inn(N), adj(N);
+    std::unordered_map<uint64_t, int> id;
+    auto add_edge = [&](int u, int x, int slot) {
+        auto it = id.find(key(u, x));
+        if (it != id.end()) return it->second;
+        const int e = (int)P.edges.size();
+        id[key(u, x)] = e;
+        P.edges.push_back({u, x});
+        P.orig_slot.push_back(slot);
+        P.tris.emplace_back();
+        out[u].insert(x); inn[x].insert(u); adj[u].insert(x); adj[x].insert(u);
+        return e;
+    };
+    for (int v = 0; v < N; ++v)
+        for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k) add_edge(in_src[k], v, k);
+    (void)E;
+    P.rank.assign(N, -1);
+    P.parent.assign(N, N);
+    std::vector<char> alive(N, 1);
+    int remaining = N;
+    std::vector<int> cand;
+    while (remaining > 0) {
+        cand.clear();
+        int mind = 1 << 30;
+        for (int v = 0; v < N; ++v)
+            if (alive[v]) { cand.push_back(v); mind = std::min(mind, (int)adj[v].size()); }
+        const int thr = std::max(mind, 2);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
+        std::vector<int> chosen;
+        std::vector<char> blocked(N, 0);
+        for (int v : cand) {
+            if ((int)adj[v].size() > thr) break;
+            if (blocked[v]) continue;
+            chosen.push_back(v);
+            for (int u : adj[v]) blocked[u] = 1;
+        }
+        for (int v : chosen) {
+            alive[v] = 0;
+            --remaining;
+            P.rank[v] = (int)P.order.size();
+            P.order.push_back(v);
+            // v leaves the alive graph: its neighbours drop it, then get pairwise shortcuts
+            for (int u : adj[v]) adj[u].erase(v);
+            std::vector<int> ins, outs;
+            for (int u : inn[v]) if (alive[u]) ins.push_back(u);
+            for (int x : out[v]) if (alive[x]) outs.push_back(x);
+            for (int u : ins)
+                for (int x : outs)
+                    if (u != x) {
+                        const int a = id[key(u, v)], b = id[key(v, x)];
+                        const int e = add_edge(u, x, -1);
+                        P.tris[e].push_back({a, b});
+                    }
+        }
+    }
+    // elimination-tree parent = lowest-ranked higher neighbour (either direction)
+    for (size_t e = 0; e < P.edges.size(); ++e) {
+        int u = P.edges[e].first, x = P.edges[e].second;
+        int lo = P.rank[u] < P.rank[x] ? u : x, hi = lo == u ? x : u;
+        if (P.parent[lo] == N || P.rank[hi] < P.rank[P.parent[lo]]) P.parent[lo] = hi;
+    }
+    P.F = (int)P.edges.size();
+    return P;
+}
+
+struct DownLayout {
+    std::vector<uint32_t> desc;     // per batch: in-degree | 0x10000 if a warp barrier must precede it
+    std::vector<uint16_t> node;     // per batch 32 destination slots
+    std::vector<uint16_t> tail;     // ELL tails
+    std::vector<int> edge_pos;      // W position of every down edge (by edge id), -1 otherwise
+    int slots = 0, wlen = 0;
+    long cost = 0;
+};
+
+// Layout of the down sweep.  Nodes of one level are independent; a level with few, high-degree nodes
+// would leave most lanes idle, so per level the in-edges of a node may be split into chunks of c edges
+// that go to partial slots first (the node then combines its partials through zero-weight entries in a
+// sub-level of its own).  c is chosen per level by the instruction-count model of the sweep:
+// 10 + 9 x degree per batch of 32 destinations, 3 per barrier.
+struct Item { int key, dest; std::vector<std::pair<int, int>> in; };   // in: (tail slot, edge id or -1 = zero weight)
+
+long batches_cost(std::vector<int> degs)
+{
+    std::sort(degs.begin(), degs.end(), std::greater<int>());
+    long cost = 0;
+    for (size_t i = 0; i < degs.size(); i += 32) cost += 10 + 9 * degs[i];
+    return cost;
+}
+
+DownLayout down_layout(const Plan &P)
+{
+    const int N = P.N;
+    DownLayout D;
+    D.edge_pos.assign(P.F, -1);
+    std::vector<std::vector<int>> dn(N);   // down in-edges (edge ids) per head
+    for (int e = 0; e < P.F; ++e)
+        if (P.rank[P.edges[e].first] > P.rank[P.edges[e].second]) dn[P.edges[e].second].push_back(e);
+    std::vector<int> level(N, 0);
+    int max_level = 0;
+    for (int r = N - 1; r >= 0; --r) {
+        const int v = P.order[r];
+        int l = 0;
+        for (int e : dn[v]) l = std::max(l, level[P.edges[e].first] + 1);
+        level[v] = l;
+        max_level = std::max(max_level, l);
+    }
+    std::vector<std::vector<int>> by_level(max_level + 1);
+    for (int v = 0; v < N; ++v)
+        if (!dn[v].empty()) by_level[level[v]].push_back(v);
+    std::vector<Item> items;
+    int next_slot = N + 1;   // slot N = +inf
+    for (int l = 1; l <= max_level; ++l) {
+        const std::vector<int> &nodes = by_level[l];
+        int maxd = 0;
+        for (int v : nodes) maxd = std::max(maxd, (int)dn[v].size());
+        int best_c = maxd;
+        long best_cost = -1;
+        for (int c = 1; c <= maxd; ++c) {
+            std::vector<int> first, second;
+            for (int v : nodes) {
+                const int d = (int)dn[v].size();
+                if (d > c) {
+                    for (int i = 0; i < d; i += c) first.push_back(std::min(c, d - i));
+                    second.push_back((d + c - 1) / c);
+                } else {
+                    first.push_back(d);
+                }
+            }
+            const long cost = batches_cost(first) + (second.empty() ? 0 : 3 + batches_cost(second));
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+        }
+        for (int v : nodes) {
+            const int d = (int)dn[v].size();
+            if (d > best_c) {
+                Item comb{l * 2 + 1, v, {}};
+                for (int i = 0; i < d; i += best_c) {
+                    Item part{l * 2, next_slot, {}};
+                    for (int j = i; j < std::min(d, i + best_c); ++j) part.in.push_back({P.edges[dn[v][j]].first, dn[v][j]});
+                    comb.in.push_back({next_slot, -1});
+                    ++next_slot;
+                    items.push_back(std::move(part));
+                }
+                items.push_back(std::move(comb));
+            } else {
+                Item it{l * 2, v, {}};
+                for (int e : dn[v]) it.in.push_back({P.edges[e].first, e});
+                items.push_back(std::move(it));
+            }
+        }
+    }
+    D.slots = next_slot;
+    std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
+        return a.key != b.key ? a.key < b.key : a.in.size() > b.in.size();
+    });
+    int prev_key = -1;
+    for (size_t i = 0; i < items.size();) {
+        size_t j = i;
+        while (j < items.size() && j - i < 32 && items[j].key == items[i].key) ++j;
+        const int deg = (int)items[i].in.size();
+        D.desc.push_back((uint32_t)deg | (items[i].key != prev_key && prev_key >= 0 ? 0x10000u : 0u));
+        prev_key = items[i].key;
+        const int base = (int)D.tail.size();
+        D.tail.resize(base + deg * 32, (uint16_t)N);   // padding: tail = the +inf slot, weight 0
+        for (int l = 0; l < 32; ++l) {
+            if (i + l < j) {
+                const Item &it = items[i + l];
+                D.node.push_back((uint16_t)it.dest);
+                for (int t = 0; t < (int)it.in.size(); ++t) {
+                    D.tail[base + t * 32 + l] = (uint16_t)it.in[t].first;
+                    if (it.in[t].second >= 0) D.edge_pos[it.in[t].second] = base + t * 32 + l;
+                }
+            } else {
+                D.node.push_back((uint16_t)N);   // idle lane: min(+inf, +inf + 0) back into the +inf slot
+            }
+        }
+        D.cost += 10 + 9 * deg + ((D.desc.back() & 0x10000u) ? 3 : 0);
+        i = j;
+    }
+    D.wlen = (int)D.tail.size();
+    return D;
+}
+
+template <typename T>
+int up(T **dst, const std::vector<T> &src)
+{
+    const size_t bytes = std::max<size_t>(src.size(), 1) * sizeof(T);
+    B200_CUDA(cudaMalloc((void **)dst, bytes));
+    if (!src.empty()) B200_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Everything the kernel reads, as host vectors (uploaded by b200_cch_prepare, replayed on the host by
+// b200_cch_host_sssp).
+struct Tables {
+    std::vector<uint32_t> dn_desc, cz_init, cz_desc, cz_tab;
+    std::vector<uint16_t> dn_node, dn_tail, uo_ptr, uo_head, parent;
+    int F = 0, wd = 0, wu = 0, slots = 0, tris = 0;
+};
+
+// false: the network is outside the 16-bit limits of the tables
+bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, Tables &T)
+{
+    if (N >= 65000 || E >= 65000) return false;
+    Plan P = make_plan(N, E, in_ptr, in_src);
+    DownLayout D = down_layout(P);
+    // up region: out-edges to higher-ranked heads, CSR by tail
+    std::vector<int> pos(P.F, -1);
+    std::vector<std::vector<int>> uo(N);
+    for (int e = 0; e < P.F; ++e)
+        if (P.rank[P.edges[e].first] < P.rank[P.edges[e].second]) uo[P.edges[e].first].push_back(e);
+    int nu = 0;
+    for (int v = 0; v < N; ++v) nu += (int)uo[v].size();
+    const long wtot = (long)D.wlen + nu;
+    if (wtot + 2 >= 65535 || D.slots >= 65535) return false;
+    T.uo_ptr.assign(N + 1, 0);
+    for (int v = 0; v < N; ++v) {
+        T.uo_ptr[v] = (uint16_t)T.uo_head.size();
+        for (int e : uo[v]) {
+            pos[e] = D.wlen + (int)T.uo_head.size();
+            T.uo_head.push_back((uint16_t)P.edges[e].second);
+        }
+    }
+    T.uo_ptr[N] = (uint16_t)T.uo_head.size();
+    for (int e = 0; e < P.F; ++e)
+        if (D.edge_pos[e] >= 0) pos[e] = D.edge_pos[e];
+    const uint32_t INFPOS = (uint32_t)wtot, DUMMY = (uint32_t)wtot + 1;
+    // customization: initial value of every filled edge, then rows of 32 edges per level
+    T.cz_init.resize(P.F);
+    for (int e = 0; e < P.F; ++e)
+        T.cz_init[e] = (uint32_t)pos[e] | ((uint32_t)(P.orig_slot[e] >= 0 ? P.orig_slot[e] : 0xFFFF) << 16);
+    std::vector<int> lvl(P.F, 0), by_low(P.F);
+    std::iota(by_low.begin(), by_low.end(), 0);
+    auto low = [&](int e) { return std::min(P.rank[P.edges[e].first], P.rank[P.edges[e].second]); };
+    std::stable_sort(by_low.begin(), by_low.end(), [&](int a, int b) { return low(a) < low(b); });
+    int max_lvl = 0;
+    for (int e : by_low) {
+        int l = 0;
+        for (auto &t : P.tris[e]) l = std::max(l, 1 + std::max(lvl[t.first], lvl[t.second]));
+        lvl[e] = l;
+        max_lvl = std::max(max_lvl, l);
+    }
+    for (int L = 1; L <= max_lvl; ++L) {   // desc: T | 0x10000 if a CTA barrier must precede the row
+        std::vector<int> es;
+        for (int e = 0; e < P.F; ++e)
+            if (lvl[e] == L) es.push_back(e);
+        std::stable_sort(es.begin(), es.end(), [&](int a, int b) { return P.tris[a].size() > P.tris[b].size(); });
+        for (size_t i = 0; i < es.size(); i += 32) {
+            const size_t j = std::min(es.size(), i + 32);
+            const int nt = (int)P.tris[es[i]].size();
+            T.cz_desc.push_back((uint32_t)nt | (i == 0 ? 0x10000u : 0u));
+            for (int l = 0; l < 32; ++l) T.cz_tab.push_back(i + l < j ? (uint32_t)pos[es[i + l]] : DUMMY);
+            for (int t = 0; t < nt; ++t)
+                for (int l = 0; l < 32; ++l) {
+                    uint32_t w = INFPOS | (INFPOS << 16);
+                    if (i + l < j && t < (int)P.tris[es[i + l]].size()) {
+                        const auto &tr = P.tris[es[i + l]][t];
+                        w = (uint32_t)pos[tr.first] | ((uint32_t)pos[tr.second] << 16);
+                        ++T.tris;
+                    }
+                    T.cz_tab.push_back(w);
+                }
+        }
+    }
+    T.parent.resize(N);
+    for (int v = 0; v < N; ++v) T.parent[v] = (uint16_t)P.parent[v];
+    T.dn_desc = std::move(D.desc);
+    T.dn_node = std::move(D.node);
+    T.dn_tail = std::move(D.tail);
+    T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots;
+    return true;
+}
+
+// CSC (in-links by head, ascending tail) of a link list, as b200_graph_create builds it
+void make_csc(int N, int E, const int32_t *row, const int32_t *col, std::vector<int32_t> &in_ptr,
+              std::vector<int32_t> &in_src, std::vector<int32_t> &in_eid)
+{
+    std::vector<int32_t> order(E);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return col[a] != col[b] ? col[a] < col[b] : row[a] < row[b]; });
+    in_ptr.assign(N + 1, 0); in_src.resize(E); in_eid.resize(E);
+    for (int k = 0; k < E; ++k) { in_src[k] = row[order[k]]; in_eid[k] = order[k]; in_ptr[col[order[k]] + 1]++; }
+    for (int v = 0; v < N; ++v) in_ptr[v + 1] += in_ptr[v];
+}
+
+}  // namespace
+
+// Host replay of exactly the schedule the kernel executes (customization rows, up phase, down-sweep
+// batches) for one cost vector and one origin: the planner's self-check, runs without a GPU.
+// cost: fp64 [E] by link id; dist_out: fp64 [N].  stats (optional, int64[8]): filled edges, lower
+// triangles, down-region entries, up-region entries, distance slots, down batches, customization rows, 0.
+extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_t *col, const double *cost, int origin,
+                                  double *dist_out, int64_t *stats)
+{
+    B200_REQUIRE(N > 0 && E > 0 && row && col && cost && dist_out && origin >= 0 && origin < N, "bad argument");
+    std::vector<int32_t> in_ptr, in_src, in_eid;
+    make_csc(N, E, row, col, in_ptr, in_src, in_eid);
+    Tables T;
+    if (!build_tables(N, E, in_ptr.data(), in_src.data(), T)) { b200_set_error("network too large for the hierarchy tables"); return B200_EUNSUPPORTED; }
+    const double INF = INFINITY;
+    std::vector<double> W((size_t)T.wd + T.wu + 2, 0.0);
+    W[T.wd + T.wu] = INF;
+    for (int e = 0; e < T.F; ++e) {
+        const uint32_t wi = T.cz_init[e];
+        W[wi & 0xffffu] = (wi >> 16) == 0xffffu ? INF : cost[in_eid[wi >> 16]];
+    }
+    size_t off = 0;
+    for (size_t r = 0; r < T.cz_desc.size(); ++r) {
+        const int nt = (int)(T.cz_desc[r] & 0xffffu);
+        std::vector<double> acc(32);
+        for (int l = 0; l < 32; ++l) {
+            acc[l] = W[T.cz_tab[off + l]];
+            for (int t = 0; t < nt; ++t) {
+                const uint32_t tri = T.cz_tab[off + 32 * (t + 1) + l];
+                const double c = W[tri & 0xffffu] + W[tri >> 16];
+                if (c < acc[l]) acc[l] = c;
+            }
+        }
+        for (int l = 0; l < 32; ++l) W[T.cz_tab[off + l]] = acc[l];
+        off += 32 * (size_t)(nt + 1);
+    }
+    std::vector<double> d(T.slots, INF);
+    d[origin] = 0.0;
+    for (int a = origin; a < N; a = T.parent[a])
+        for (int j = T.uo_ptr[a]; j < T.uo_ptr[a + 1]; ++j) {
+            const double c = d[a] + W[T.wd + j];
+            if (c < d[T.uo_head[j]]) d[T.uo_head[j]] = c;
+        }
+    off = 0;
+    for (size_t b = 0; b < T.dn_desc.size(); ++b) {
+        const int deg = (int)(T.dn_desc[b] & 0xffffu);
+        double best[32];
+        for (int l = 0; l < 32; ++l) {
+            best[l] = d[T.dn_node[b * 32 + l]];
+            for (int j = 0; j < deg; ++j) {
+                const double c = d[T.dn_tail[off + j * 32 + l]] + W[off + j * 32 + l];
+                if (c < best[l]) best[l] = c;
+            }
+        }
+        for (int l = 0; l < 32; ++l) d[T.dn_node[b * 32 + l]] = best[l];
+        off += (size_t)deg * 32;
+    }
+    for (int v = 0; v < N; ++v) dist_out[v] = d[v];
+    if (stats) {
+        stats[0] = T.F; stats[1] = T.tris; stats[2] = T.wd; stats[3] = T.wu; stats[4] = T.slots;
+        stats[5] = (int64_t)T.dn_desc.size(); stats[6] = (int64_t)T.cz_desc.size(); stats[7] = 0;
+    }
+    return 0;
+}
+
+// Plans the hierarchy and uploads its tables; sets g->cch_ok.  Returns 0 also when the network is
+// outside the 16-bit limits of the tables (the label-correcting kernel then serves it alone).
+int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src)
+{
+    g->cch_ok = 0;
+    Tables T;
+    if (!build_tables(g->N, g->E, in_ptr, in_src, T)) return 0;
+    int rc;
+    if ((rc = up(&g->cch_dn_desc, T.dn_desc)) || (rc = up(&g->cch_dn_node, T.dn_node)) || (rc = up(&g->cch_dn_tail, T.dn_tail)) ||
+        (rc = up(&g->cch_uo_ptr, T.uo_ptr)) || (rc = up(&g->cch_uo_head, T.uo_head)) || (rc = up(&g->cch_parent, T.parent)) ||
+        (rc = up(&g->cch_cz_init, T.cz_init)) || (rc = up(&g->cch_cz_desc, T.cz_desc)) || (rc = up(&g->cch_cz_tab, T.cz_tab)))
+        return rc;
+    g->cch_F = T.F;
+    g->cch_wd = T.wd;
+    g->cch_wu = T.wu;
+    g->cch_slots = T.slots;
+    g->cch_dn_batches = (int)T.dn_desc.size();
+    g->cch_cz_rows = (int)T.cz_desc.size();
+    g->cch_tris = T.tris;
+    int e2 = 0;
+    frexp((double)g->min_t0, &e2);
+    g->cch_exact_limit = ldexp(1.0, (e2 - 1) - 23 + 52);   // labels below this are exact sums (file header)
+    g->cch_ok = 1;
+    return 0;
+}
+
+void b200_cch_destroy(b200_graph *g)
+{
+    void *ptrs[] = {g->cch_dn_desc, g->cch_dn_node, g->cch_dn_tail, g->cch_uo_ptr, g->cch_uo_head, g->cch_parent,
+                    g->cch_cz_init, g->cch_cz_desc, g->cch_cz_tab, g->cch_ws};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+}

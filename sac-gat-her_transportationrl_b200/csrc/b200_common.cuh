@@ -62,7 +62,6 @@ struct b200_graph {
     uint16_t *tree_ws;
     size_t tree_ws_bytes;
     int warm_start;   // 0 disables the warm start (env B200_NO_WARM, A/B measurements)
-    int group_lanes;     // lanes per origin group in the general fused kernel (8 or 32; env B200_GROUP)
     int cluster_limit;   // max thread-block cluster size of the general kernel (env B200_CLUSTER; 1 = off, 0 = auto)
     int last_cluster;    // cluster size of the last fused launch (tests / tools)
     int last_warps;      // warps per CTA of the last fused launch
@@ -98,6 +97,19 @@ struct b200_graph {
     void *plugin_launch;   // launcher of the on-demand plugin that matched this topology (else built-in)
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32;
+    // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): down-sweep batches
+    // (descriptor, 32 destination slots, ELL tails), up-phase CSR (out-edges to higher-ranked heads) and
+    // elimination-tree parents, customization tables (initial weight per filled edge, rows of 32 edges
+    // with their lower triangles); W positions: [0, cch_wd) down region, then cch_wu up-region entries,
+    // then the +inf and the write-only dummy slot.  cch_ws: per-CTA weight workspace in HBM for the
+    // part of W that does not fit shared memory, grown on demand like tree_ws.
+    int cch_ok, cch_F, cch_wd, cch_wu, cch_slots, cch_dn_batches, cch_cz_rows, cch_tris, cch_wmode;
+    double cch_exact_limit;
+    uint32_t *cch_dn_desc, *cch_cz_init, *cch_cz_desc, *cch_cz_tab;
+    uint16_t *cch_dn_node, *cch_dn_tail, *cch_uo_ptr, *cch_uo_head, *cch_parent;
+    double *cch_ws;
+    size_t cch_ws_bytes, smem_cch;
+    int warps_cch;
 };
 
 // ---------------------------------------------------------------------------------------------

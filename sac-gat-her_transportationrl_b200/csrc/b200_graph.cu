@@ -35,6 +35,9 @@ static int pad4(int x) { return (x + 3) & ~3; }
 
 size_t b200_fused_smem_bytes(const b200_graph *g, int prec, int warps);  // b200_assign.cu
 int b200_pick_warps(const b200_graph *g, int prec, size_t *smem_out);   // b200_assign.cu
+int b200_pick_warps_cch(b200_graph *g);                                 // b200_assign.cu
+int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src);   // b200_cch.cu
+void b200_cch_destroy(b200_graph *g);
 int b200_small_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src, const int32_t *in_eid,
                        const float *t0, int num_od, const int32_t *od_o, const int32_t *od_d, const double *od_q,
                        const int32_t *origin_slot);
@@ -131,11 +134,6 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     if (getenv("B200_NO_WARM")) g->warm_start = 0;
     if (getenv("B200_WARM")) g->warm_start = 1;
     g->cluster_limit = getenv("B200_CLUSTER") ? atoi(getenv("B200_CLUSTER")) : 0;
-    // Lanes per origin.  The device code supports sub-warp groups (8 lanes per origin, four origins
-    // per warp), but measured on the Anaheim-size network that is 3x SLOWER than a warp per origin:
-    // the kernel is bound by the latency of each origin's dependent chain, and the O(N) passes
-    // (initialisation, predecessor selection, leaf scan) get four times as many steps.
-    g->group_lanes = 32;
     g->N = N; g->E = E; g->O = O; g->num_od = num_od; g->max_in_deg = max_in; g->total_demand = total;
     B200_CUDA(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -197,6 +195,9 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
     std::copy(origins.begin(), origins.end(), g->origins_host);
     b200_small_prepare(g, in_ptr.data(), in_src.data(), in_eid.data(), t0, num_od, od_o, od_d, od_q, origin_slot.data());
     b200_static_prepare(g, row, col, t0, cap0, num_od, od_o, od_d, od_q, origin_slot.data());
+    if ((rc = b200_cch_prepare(g, in_ptr.data(), in_src.data()))) { b200_graph_destroy(g); return rc; }
+    if (g->cch_ok && getenv("B200_CCH_LIMIT")) g->cch_exact_limit = atof(getenv("B200_CCH_LIMIT"));   // test hook: force the fallback
+    b200_pick_warps_cch(g);
     g->warps_f32 = b200_pick_warps(g, B200_F32, &g->smem_f32);
     g->warps_f64 = b200_pick_warps(g, B200_F64, &g->smem_f64);
     if (g->warps_f32 <= 0 || g->warps_f64 <= 0) {
@@ -218,6 +219,7 @@ extern "C" int b200_graph_destroy(b200_graph *g)
                     g->tree_ws, g->topo16, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    b200_cch_destroy(g);
     free(g->origins_host);
     delete g;
     return 0;

@@ -7,11 +7,15 @@ transition is a fixed-size record and the buffer is a set of preallocated ``[cap
 tensors: adding a batch is one indexed copy per field, a sampled batch is a gather, batch assembly
 is a reshape.  Semantics kept from the reference:
 
-* priority ``p = (|td| + eps) ** alpha``; new items get the running maximum priority (:50-58);
+* priority ``p = (|td| + eps) ** alpha``; new items get the running maximum priority, and - like the
+  reference's ``add`` (:50-58), which passes the maximum through ``abs(.) + eps`` and takes the maximum
+  again - every default-priority insert raises the running maximum by ``eps``;
 * sampling proportional to ``p`` with replacement (the sum-tree descent of :63-79 draws
   ``batch_size`` independent uniforms), importance weights ``(size * p / total) ** -beta``
   normalised by their maximum (:80-82);
-* ``update_priorities`` with the learner's TD errors (:86-91);
+* ``update_priorities`` with the learner's TD errors (:86-91): the reference loops over the sampled
+  indices in order, so for an index drawn twice the LAST occurrence wins - reproduced
+  deterministically (stable sort, keep the last of each run), never by a racing scatter;
 * hindsight relabelling of a sampled item (:808-830): goal := links already repaired in the next
   state, reward recomputed for that goal, done := goal complete, goal column of the edge
   features overwritten.
@@ -49,8 +53,13 @@ class DeviceReplay:
             "initial_tstt": torch.zeros((capacity,), dtype=torch.float64, device=dev),
         }
         self.priority = torch.zeros((capacity,), dtype=torch.float32, device=dev)  # already ** alpha
-        self.max_priority = 1.0
+        self._max_priority = torch.ones((), dtype=torch.float64, device=dev)    # on the device: no sync per update
         self.ptr, self.size = 0, 0
+
+    @property
+    def max_priority(self) -> float:
+        """Running maximum of ``|td| + eps`` (reference attribute of the same name); reading it syncs."""
+        return float(self._max_priority)
 
     def bytes_per_transition(self) -> int:
         return sum(t.element_size() * (t.numel() // self.capacity) for t in self.store.values()) + 4
@@ -69,12 +78,14 @@ class DeviceReplay:
         for k, dst in self.store.items():
             dst[slots] = batch[k].to(device=self.device, dtype=dst.dtype)
         if priority is None:
-            p = torch.full((n,), (abs(self.max_priority) + self.eps) ** self.alpha, dtype=torch.float32,
-                           device=self.device)
+            # n sequential reference adds: item i enters at max + (i + 1) eps, which becomes the new maximum
+            steps = torch.arange(1, n + 1, dtype=torch.float64, device=self.device)
+            p = ((self._max_priority + steps * self.eps) ** self.alpha).float()
+            self._max_priority = self._max_priority + n * self.eps
         else:
-            pr = priority.abs().float() + self.eps
-            self.max_priority = max(self.max_priority, float(pr.max()))
-            p = pr ** self.alpha
+            pr = priority.abs().double().to(self.device)[-n:] + self.eps
+            self._max_priority = torch.maximum(self._max_priority, pr.max())
+            p = (pr ** self.alpha).float()
         self.priority[slots] = p
         self.ptr = (self.ptr + n) % self.capacity
         self.size = min(self.size + n, self.capacity)
@@ -96,10 +107,15 @@ class DeviceReplay:
         return batch, idx, weights.float()
 
     def update_priorities(self, idx: torch.Tensor, td_errors: torch.Tensor) -> None:
-        pr = td_errors.detach().abs().float().to(self.device) + self.eps
-        self.max_priority = max(self.max_priority, float(pr.max())) if pr.numel() else self.max_priority
-        # duplicates in idx: last writer wins, as in the reference's sequential loop
-        self.priority[idx] = pr ** self.alpha
+        if idx.numel() == 0:
+            return
+        pr = td_errors.detach().abs().double().to(self.device) + self.eps
+        self._max_priority = torch.maximum(self._max_priority, pr.max())
+        # an index sampled more than once: the reference's sequential loop leaves the LAST one in place
+        sidx, perm = torch.sort(idx.to(self.device), stable=True)
+        last = torch.ones_like(sidx, dtype=torch.bool)
+        last[:-1] = sidx[1:] != sidx[:-1]
+        self.priority[sidx[last]] = (pr[perm[last]] ** self.alpha).float()
 
     # ---- hindsight relabelling ------------------------------------------------------------------
     @staticmethod

@@ -679,3 +679,74 @@ def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, n
     steep = _engine(b200env, sf_graph, "fp32", bpr_beta=9.0)
     out = _assign(steep, masks[:4], 5, "fw")
     assert steep.last_config["cch"] == 0 and np.all(np.isfinite(out["tstt"]))
+
+
+@pytest.mark.parametrize("which,B,K", [("an", 48, 20), ("cs", 6, 8)])
+def test_general_kernel_hierarchy_equals_label_correcting_and_oracle(b200env, native_lib, monkeypatch, which, B, K):
+    """The general fused kernel takes fp32 shortest paths from the contraction hierarchy (b200_cch.cu:
+    customization + up phase + static down sweep); B200_NO_CCH forces frontier label correcting and
+    B200_CCH_LIMIT=1 makes every origin fail the exactness bound, i.e. take the in-kernel Bellman-Ford
+    fallback.  All three - and the C oracle - must agree bit for bit, for every method; fp64 link state
+    keeps label correcting."""
+    from oracle.c_oracle import COracle
+    g = b200env.synthetic.anaheim_size(0) if which == "an" else b200env.synthetic.chicago_sketch_size(0)
+    orc = COracle.from_graph_data(g)
+    masks = _damage_batch(len(g.edges), B, seed=11)
+    cch = _engine(b200env, g, "fp32")
+    monkeypatch.setenv("B200_NO_CCH", "1")
+    lc = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_NO_CCH")
+    monkeypatch.setenv("B200_CCH_LIMIT", "1.0")
+    fb = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_CCH_LIMIT")
+    for method in ("fw", "msa", "cfw"):
+        a = _assign(cch, masks, K, method)
+        assert cch.last_config["cch"] == 1 and cch.kernel_name == "assign_fused_kernel"
+        b = _assign(lc, masks, K, method)
+        assert lc.last_config["cch"] == 0
+        c = _assign(fb, masks[:4], K, method)
+        for key in ("flow", "tstt", "unassigned", "status"):
+            assert np.array_equal(a[key], b[key]), (method, key)
+            assert np.array_equal(a[key][:4], c[key]), (method, key, "fallback")
+        # the gap is a block-wide fp64 sum: its last bits follow the warps per CTA, which differ between the paths
+        np.testing.assert_allclose(a["gap"], b["gap"], rtol=1e-12)
+        np.testing.assert_allclose(a["gap"][:4], c["gap"], rtol=1e-12)
+        if method != "cfw":
+            _assert_bit_equal_to_oracle(a, orc, masks, range(0, B, max(1, B // 6)), K, method, f"{which} hierarchy")
+    # warm start from a previous result
+    a = _assign(cch, masks, K, "fw")
+    a2, b2 = _assign(cch, masks, 5, "fw", flow0=a["flow"]), _assign(lc, masks, 5, "fw", flow0=a["flow"])
+    assert np.array_equal(a2["flow"], b2["flow"]) and np.array_equal(a2["tstt"], b2["tstt"])
+    f64 = _engine(b200env, g, "fp64")
+    _assign(f64, masks[:2], 3, "fw")
+    assert f64.last_config["cch"] == 0
+
+
+def test_general_kernel_hierarchy_on_a_network_with_dead_ends(b200env, native_lib, monkeypatch):
+    """One-way links, a node nobody can reach and demand to it: the hierarchy path must report the same
+    unassigned demand / penalty TSTT as label correcting and the oracle (reference :496-500, :730-732)."""
+    from oracle.c_oracle import COracle
+    E = b200env.EdgeData
+    rng = np.random.default_rng(8)
+    n = 70   # > 64 nodes: not a small-network kernel case
+    links = {(i, i + 1) for i in range(1, n - 1)} | {(i + 1, i) for i in range(1, n - 1) if i % 3}
+    links |= {(int(a), int(b)) for a, b in rng.integers(1, n, size=(60, 2)) if a != b}
+    links = sorted(links)   # node n has no in-link at all
+    g = b200env.GraphData(num_nodes=n, edges=[E(u, v, 900.0, float(1 + (u * 7 + v) % 5), float(1 + (u * 7 + v) % 5), 0.15, 4.0)
+                                               for u, v in links],
+                          od_demand={(int(o), int(d)): float(10 * (1 + (o + d) % 4)) for o in (1, 5, 9, 30, 44)
+                                     for d in (2, 17, 33, 52, n)})
+    orc = COracle.from_graph_data(g)
+    masks = _damage_batch(len(links), 6, seed=5, ratio=0.2)
+    cch = _engine(b200env, g, "fp32", unassigned_penalty=1e4)
+    monkeypatch.setenv("B200_NO_CCH", "1")
+    lc = _engine(b200env, g, "fp32", unassigned_penalty=1e4)
+    monkeypatch.delenv("B200_NO_CCH")
+    a, b = _assign(cch, masks, 10, "msa"), _assign(lc, masks, 10, "msa")
+    assert cch.kernel_name == "assign_fused_kernel" and cch.last_config["cch"] == 1
+    for key in ("flow", "tstt", "unassigned", "status"):
+        assert np.array_equal(a[key], b[key]), key
+    assert np.all(a["unassigned"] > 0) and np.all(a["status"] & 2)
+    for s in range(6):
+        o = orc.assign(masks[s], None, 10, "msa", penalty=1e4)
+        assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"] and a["unassigned"][s] == o["unassigned"]

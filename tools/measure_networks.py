@@ -47,7 +47,7 @@ def main():
             torch.cuda.synchronize()
             ms = s.elapsed_time(e) / reps
             bytes_per = K * ((33 if precision == "fp32" else 65) * eng.E + 8 * eng.O * eng.N)
-            print(json.dumps({"network": name, "kernel": eng.kernel_name, "cluster_env": os.environ.get("B200_CLUSTER", "auto"), "N": eng.N, "E": eng.E, "O": eng.O, "B": B, "K": K, "method": method,
+            print(json.dumps({"network": name, "kernel": eng.kernel_name, "config": eng.last_config, "cluster_env": os.environ.get("B200_CLUSTER", "auto"), "N": eng.N, "E": eng.E, "O": eng.O, "B": B, "K": K, "method": method,
                               "precision": precision, "ms": round(ms, 3), "assignments_per_s": round(B / ms * 1e3, 1),
                               "algorithmic_GBps": round(bytes_per * B / ms / 1e6, 2),
                               "median_gap": float(out["gap"].median())}), flush=True)
