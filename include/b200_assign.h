@@ -138,6 +138,15 @@ int b200_state_features(const b200_graph *g, int B, int prec, const void *flow, 
  * status word for out-of-range actions (reference raises ValueError, :208-209). */
 int b200_apply_actions(const b200_graph *g, int B, const int32_t *action, uint8_t *dmg, uint8_t *valid,
                        int32_t *status, void *stream);
+/* reset() damage sampling on the device (reference :167-190): for every row with select[b] != 0
+ * (select NULL = all rows) draw `count` distinct damaged links, retrying up to max_tries times until the
+ * undamaged links form a strongly connected subgraph on the nodes they touch, then one unconstrained
+ * draw (the reference's rule, max_tries = 50).  dmg uint8 [B][E] rows are overwritten; counters uint64 [B]
+ * (device, in/out) is the per-scenario position in a counter-based random stream keyed by `seed` - NOT
+ * numpy's Generator stream: masks that must equal the reference's draw for a seed are sampled on the host
+ * (env/network.py) and passed in.  tries int32 [B] (optional): tries used, max_tries + 1 = unconstrained. */
+int b200_sample_damage(const b200_graph *g, int B, int count, int max_tries, uint64_t seed, uint64_t *counters,
+                       const uint8_t *select, uint8_t *dmg, int32_t *tries, void *stream);
 /* reward_mode: 0 delta, 1 log_delta, 2 neg_tstt, 3 minimize_tstt, 4 rel_improve (reference :256-291) */
 int b200_reward_done(const b200_graph *g, int B, int reward_mode, const double *prev_tstt, const double *tstt,
                      const double *initial_tstt, const uint8_t *dmg, const uint8_t *goal, const uint8_t *valid,

@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 EXPORTS = [
     "b200_last_error", "b200_version", "b200_graph_create", "b200_graph_destroy", "b200_graph_info",
     "b200_graph_origins", "b200_bpr", "b200_sssp", "b200_aon", "b200_update_reduce", "b200_assign",
-    "b200_assign_launches", "b200_assign_last_config", "b200_cch_host_sssp", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_reward_done",
+    "b200_assign_launches", "b200_assign_last_config", "b200_cch_host_sssp", "b200_assign_kernel_name", "b200_register_static_plugin", "b200_state_features", "b200_apply_actions", "b200_sample_damage", "b200_reward_done",
     "b200_gat_edge_softmax_aggregate_fwd", "b200_gat_edge_softmax_aggregate_bwd",
 ]
 
@@ -124,6 +124,7 @@ def _declare(lib) -> None:
     lib.b200_register_static_plugin.argtypes = [C.c_char_p]
     lib.b200_state_features.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp]
     lib.b200_apply_actions.argtypes = [_vp, _i, _vp, _vp, _vp, _vp, _vp]
+    lib.b200_sample_damage.argtypes = [_vp, _i, _i, _i, C.c_uint64, _vp, _vp, _vp, _vp, _vp]
     lib.b200_reward_done.argtypes = [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp]
     lib.b200_gat_edge_softmax_aggregate_fwd.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp]
     lib.b200_gat_edge_softmax_aggregate_bwd.argtypes = [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp,

@@ -45,6 +45,7 @@ struct Cta {
     // cch_wd and wu[pos - cch_wd] from there on (the +inf and dummy slots follow the up region)
     double *wd, *wu;
     int cch_wd;
+    bool lean;   // per-warp scratch without the second queue / counters (warp_offsets)
 
     // link load of link e as REAL, whatever the accumulation type
     __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
@@ -55,7 +56,8 @@ struct Cta {
         const int wmode = cch ? p.cch.wmode : 0;
         const size_t w_smem = !cch ? 0 : (wmode == 2 ? (size_t)(p.cch.wd + p.cch.wu + 2) * 8 : wmode == 1 ? (size_t)p.cch.wd * 8 : 0);
         SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt, cch ? p.cch.slots : 0,
-                                   w_smem);
+                                   w_smem, cch && p.kahn_pack);
+        lean = cch && p.kahn_pack;
         if (cch) {
             double *ws_cta = p.cch.ws + (size_t)blockIdx.x * p.cch.ws_stride;
             double *sm = (double *)(smem + L.off_cchw);
@@ -139,7 +141,7 @@ struct WarpScratch {
 template <typename REAL>
 __device__ __forceinline__ WarpScratch warp_scratch(const Cta<REAL> &c, int warp, int dist_slots = 0)
 {
-    const WarpOffsets W = warp_offsets(c.N, c.alias_cnt, dist_slots);
+    const WarpOffsets W = warp_offsets(c.N, c.alias_cnt, dist_slots, c.lean);
     unsigned char *base = c.warp_base + c.warp_stride * warp;
     WarpScratch s;
     s.dist = (double *)base;
@@ -306,16 +308,21 @@ __device__ void warp_select_pred(const Cta<REAL> &c, int origin, const WarpScrat
     const double *__restrict__ w = c.w;
     for (int v = lane; v < N; v += 32) {
         const double dv = dist[v];
-        int bk = kNoPk, bu = -1;
+        int bk = kNoPk;
         double bdu = B200_INF_F64;
         if (v != origin && dv < B200_INF_F64) {
+            // in-links come by ascending tail id, so "<=" on dist[u] leaves the largest u among equals
             const int k1 = in_ptr[v + 1];
-            for (int k = in_ptr[v]; k < k1; ++k) {
-                const int u = in_src[k];
-                const double du = dist[u];
-                if (du + w[k] == dv && (bk == kNoPk || du < bdu || (du == bdu && u > bu))) {
-                    bk = k; bu = u; bdu = du;
-                }
+            int k = in_ptr[v];
+            for (; k + 2 <= k1; k += 2) {
+                const double du0 = dist[in_src[k]], du1 = dist[in_src[k + 1]];
+                const double c0 = du0 + w[k], c1 = du1 + w[k + 1];
+                if (c0 == dv && du0 <= bdu) { bk = k; bdu = du0; }
+                if (c1 == dv && du1 <= bdu) { bk = k + 1; bdu = du1; }
+            }
+            if (k < k1) {
+                const double du0 = dist[in_src[k]];
+                if (du0 + w[k] == dv && du0 <= bdu) bk = k;
             }
         }
         s.pk[v] = (uint16_t)bk;
@@ -389,45 +396,74 @@ __device__ int warp_sssp_bf(const Cta<REAL> &c, int origin, const WarpScratch &s
     return 1;
 }
 
-// One warp, one origin: up phase along the elimination-tree ancestors of the origin, then the static
-// down sweep over the ELL batches (see b200_cch.cu); labels are exact sums, checked below.
+// Row-stream engine: calls f(word, flag) for every row of a stream ([nrows][32] words, one flag byte per
+// row, nrows a multiple of 8; see b200_cch.cu).  The rows are read strictly in order, so each lane keeps
+// the next 8 words of its column in registers: by the time a row is processed its load was issued 8 rows
+// earlier, which hides L1, L2 and HBM latency alike - the tables need not fit shared memory.
+template <class F>
+__device__ __forceinline__ void stream_rows(const uint32_t *__restrict__ rows, const uint8_t *__restrict__ flags, int nrows,
+                                            F &&f)
+{
+    if (nrows <= 0) return;
+    const uint32_t *rp = rows + (threadIdx.x & 31);
+    uint32_t ring[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ring[i] = __ldg(rp + i * 32);
+    uint2 fl = __ldg((const uint2 *)flags);
+    for (int s = 0; s < nrows; s += 8) {
+        const bool more = s + 8 < nrows;
+        const uint2 fnext = more ? __ldg((const uint2 *)(flags + s + 8)) : make_uint2(0u, 0u);
+        rp += 256;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t e = ring[i];
+            if (more) ring[i] = __ldg(rp + i * 32);
+            f(e, ((i < 4 ? fl.x : fl.y) >> (8 * (i & 3))) & 0xffu);
+        }
+        fl = fnext;
+    }
+}
+
+// One warp, one origin: up stream of the origin (its elimination-tree ancestors push along their edges to
+// higher ranks), then the down stream shared by all origins (b200_cch.cu); labels are exact sums, checked below.
 template <typename REAL>
-__device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int origin, const WarpScratch &s)
+__device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
     const CchParams &h = p.cch;
     const int lane = threadIdx.x & 31, N = c.N;
     double *dist = s.dist;
     for (int v = lane; v < h.slots; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
-    __syncwarp();
-    const double *__restrict__ wu = c.wu;
-    for (int a = origin; a < N; a = __ldg(h.parent + a)) {
-        const double da = dist[a];   // final: every lower ancestor has pushed already
-        if (da < B200_INF_F64) {
-            const int j1 = __ldg(h.uo_ptr + a + 1);
-            for (int j = __ldg(h.uo_ptr + a) + lane; j < j1; j += 32) {
-                const int x = __ldg(h.uo_head + j);
-                const double cand = da + wu[j];
-                if (cand < dist[x]) dist[x] = cand;
+    {
+        const double *__restrict__ wu = c.wu;
+        const uint32_t r0 = __ldg(h.up_off + slot), r1 = __ldg(h.up_off + slot + 1);
+        double da = B200_INF_F64;
+        stream_rows(h.up_rows + (size_t)r0 * 32, h.up_flags + r0, (int)(r1 - r0), [&](uint32_t e, uint32_t fb) {
+            if (fb & 1u) {   // next ancestor: every lower one has pushed, its label is final
+                __syncwarp();
+                da = dist[e & 0xffffu];
+            } else {
+                const double cand = da + wu[e >> 16];
+                double *dx = dist + (e & 0xffffu);
+                if (cand < *dx) *dx = cand;
             }
-        }
-        __syncwarp();
+        });
     }
-    const double *__restrict__ wd = c.wd;
-    const uint16_t *__restrict__ tails = h.dn_tail;
-    int off = lane;
-    for (int b = 0; b < h.dn_batches; ++b) {
-        const uint32_t desc = __ldg(h.dn_desc + b);
-        const int deg = (int)(desc & 0xffffu);
-        if (desc & 0x10000u) __syncwarp();   // next level: the labels it pulls from are complete
-        const int dest = __ldg(h.dn_node + b * 32 + lane);
-        double best = dist[dest];
-#pragma unroll 4
-        for (int j = 0; j < deg; ++j) {
-            const double cand = dist[__ldg(tails + off + j * 32)] + wd[off + j * 32];
-            best = cand < best ? cand : best;
-        }
-        dist[dest] = best;
-        off += deg * 32;
+    __syncwarp();   // initial labels and the last pushes are visible to the whole warp
+    {
+        const double *__restrict__ wd = c.wd;
+        int dest = N;
+        double best = B200_INF_F64;
+        stream_rows(h.dn_rows, h.dn_flags, h.dn_nrows, [&](uint32_t e, uint32_t fb) {
+            if (fb & 1u) {   // header: destination slots of the next batch
+                if (fb & 2u) __syncwarp();   // first batch of a level: the labels it pulls from are complete
+                dest = (int)(e & 0xffffu);
+                best = (e & 0x10000u) ? B200_INF_F64 : dist[dest];   // partial slots are reused from level to level
+            } else {
+                const double cand = dist[e & 0xffffu] + wd[e >> 16];
+                best = cand < best ? cand : best;
+                if (fb & 4u) dist[dest] = best;
+            }
+        });
     }
     __syncwarp();
     unsigned mx = 0;
@@ -515,9 +551,71 @@ __device__ double warp_aon_peel(Cta<REAL> &c, const Params &p, int slot, int ori
     return un;
 }
 
+// Integer demands whose per-origin total stays below 2^28 on a network with out-degree <= 15 (every
+// shipped / generated network): ONE 32-bit word per node = children still pending << 28 | demand sum of
+// the subtree so far, so delivering a subtree to its parent is a single shared-memory atomic, and the
+// lane that delivers the LAST child keeps walking up with the parent - no ready queues, no ballots.
+// Lanes start from the leaves (lane l takes leaves l, l + 32, ..) and pick the next one when their
+// chain ends at a node that still waits for other children.
+template <typename REAL>
+__device__ double warp_aon_chain(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
+{
+    constexpr unsigned kChild = 1u << 28, kSum = kChild - 1u;
+    const int lane = threadIdx.x & 31, N = c.N;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint16_t *__restrict__ in_src = c.in_src, *__restrict__ in_eid = c.in_eid;
+    unsigned *word = (unsigned *)s.dist;   // dist is dead once pk is chosen
+    int *auxq = (int *)c.aux;
+    const REAL *q = (const REAL *)p.od_q;
+    for (int v = lane; v < N; v += 32) word[v] = 0u;
+    __syncwarp();
+    const int jd1 = __ldg(p.od_ptr + slot + 1);
+    for (int j = __ldg(p.od_ptr + slot) + lane; j < jd1; j += 32) word[__ldg(p.od_dst + j)] = (unsigned)(int)q[j];
+    __syncwarp();
+    double un = 0.0;
+    for (int v = lane; v < N; v += 32) {
+        const int k = s.pk[v];
+        if (k != kNoPk) atomicAdd(&word[in_src[k]], kChild);
+        else un += (double)(word[v] & kSum);   // unreachable destination, or demand to the origin itself (reference :496)
+    }
+    __syncwarp();
+    uint16_t *leaves = s.q0;
+    int count = 0;
+    for (int v0 = 0; v0 < N; v0 += 32) {
+        const int v = v0 + lane;
+        const bool leaf = v < N && s.pk[v] != kNoPk && word[v] < kChild;
+        const unsigned m = __ballot_sync(FULL, leaf);
+        if (leaf) leaves[count + __popc(m & lt)] = (uint16_t)v;
+        count += __popc(m);
+    }
+    __syncwarp();
+    int next = lane, v = -1;
+    unsigned sv = 0u;
+    for (;;) {
+        if (v < 0 && next < count) {
+            v = leaves[next];
+            sv = word[v];   // a leaf: no children, the word is its own demand
+            next += 32;
+        }
+        if (!__any_sync(FULL, v >= 0)) break;
+        if (v >= 0) {
+            const int k = s.pk[v], u = in_src[k];
+            if (sv != 0u) atomicAdd(&auxq[in_eid[k]], (int)sv);
+            const unsigned old = atomicAdd(&word[u], sv - kChild);
+            // the last child to arrive carries the parent's completed subtree sum upwards
+            const bool last = (old >> 28) == 1u && u != origin;
+            sv = (old + sv) & kSum;
+            v = last ? u : -1;
+        }
+    }
+    return un;
+}
+
 template <typename REAL>
 __device__ __forceinline__ double warp_aon(Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
+    if (p.kahn_pack) return warp_aon_chain<REAL>(c, p, slot, origin, s);
     return c.intq ? warp_aon_peel<REAL, true>(c, p, slot, origin, s) : warp_aon_peel<REAL, false>(c, p, slot, origin, s);
 }
 
@@ -879,7 +977,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
                 const int o = __ldg(p.origins + s);
                 const WarpScratch ws = warp_scratch(c, warp, CCH ? p.cch.slots : 0);
                 if (CCH) {
-                    capped |= warp_sssp_cch<REAL>(c, p, o, ws);
+                    capped |= warp_sssp_cch<REAL>(c, p, s, o, ws);
                 } else {
                     uint16_t *tree = p.tree_ws + ((size_t)cluster_id * p.O + s) * p.N;
                     capped |= warp_sssp<REAL>(c, o, ws, (it > 0 && p.warm) ? tree : nullptr);
@@ -935,7 +1033,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.off_in_src = g->off_in_src; p.off_in_eid = g->off_in_eid;
     p.topo16 = g->topo16; p.topo16_bytes = g->topo16_bytes; p.o16_in_src = g->o16_in_src; p.o16_in_eid = g->o16_in_eid;
     p.o16_out_ptr = g->o16_out_ptr; p.o16_out_dst = g->o16_out_dst;
-    p.intq = g->gen_intq; p.warm = g->warm_start;
+    p.intq = g->gen_intq; p.warm = g->warm_start; p.kahn_pack = g->kahn_pack;
     p.alias32 = gen_alias(g, 4); p.alias64 = gen_alias(g, 8);
     p.topo = g->topo; p.row = g->row; p.origins = g->origins; p.od_ptr = g->od_ptr; p.od_dst = g->od_dst;
     p.t0_csc = g->t0_csc; p.cap0_csc = g->cap0_csc; p.t0 = g->t0; p.cap0 = g->cap0;
@@ -945,11 +1043,11 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.st_origpos = g->st_origpos;
     p.total_demand = g->total_demand;
     if (g->cch_ok) {
-        p.cch.dn_desc = g->cch_dn_desc; p.cch.cz_init = g->cch_cz_init; p.cch.cz_desc = g->cch_cz_desc;
-        p.cch.cz_tab = g->cch_cz_tab; p.cch.dn_node = g->cch_dn_node; p.cch.dn_tail = g->cch_dn_tail;
-        p.cch.uo_ptr = g->cch_uo_ptr; p.cch.uo_head = g->cch_uo_head; p.cch.parent = g->cch_parent;
+        p.cch.dn_rows = g->cch_dn_rows; p.cch.dn_flags = g->cch_dn_flags; p.cch.up_rows = g->cch_up_rows;
+        p.cch.up_flags = g->cch_up_flags; p.cch.up_off = g->cch_up_off; p.cch.cz_init = g->cch_cz_init;
+        p.cch.cz_desc = g->cch_cz_desc; p.cch.cz_tab = g->cch_cz_tab;
         p.cch.F = g->cch_F; p.cch.wd = g->cch_wd; p.cch.wu = g->cch_wu; p.cch.slots = g->cch_slots;
-        p.cch.dn_batches = g->cch_dn_batches; p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
+        p.cch.dn_nrows = g->cch_dn_nrows; p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
         union { double d; unsigned long long u; } lim;
         lim.d = g->cch_exact_limit;
         p.cch.exact_hi = (unsigned)(lim.u >> 32);
@@ -1091,14 +1189,15 @@ int b200_pick_warps_cch(b200_graph *g)
         if (forced_m >= 0 && mode != forced_m) continue;
         const size_t wb = mode == 2 ? (size_t)(g->cch_wd + g->cch_wu + 2) * 8 : mode == 1 ? (size_t)g->cch_wd * 8 : 0;
         for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-            SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, 4, true, g->cch_slots, wb);
+            SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, 4, true, g->cch_slots, wb, g->kahn_pack != 0);
             if (L.total > kSmemLimit) break;
             if (forced_w && w != forced_w) continue;
             const int O = std::max(g->O, 1);
             const double eff = (double)O / (double)(((O + w - 1) / w) * w);
             const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
-            // resident warps, with a premium for weights in shared memory (every origin streams the down region)
-            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 1.25 : mode == 1 ? 1.15 : 1.0);
+            // resident warps, with a premium for weights in shared memory: every origin gathers from the whole
+            // down region, and the up phase is a chain of dependent reads (L2 latency per ancestor otherwise)
+            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 2.0 : mode == 1 ? 1.6 : 1.0);
             if (score > best_score + 1e-9) { best_score = score; best_w = w; best_m = mode; best_smem = L.total; }
         }
     }

@@ -31,7 +31,7 @@ struct WarpOffsets {
 // dead dist[] array and the pending-children counters go into the upper half
 // dist_slots: the contraction-hierarchy sweeps keep N labels, the +inf slot and the partial slots of split
 // destinations in the distance array (0 = N, the label-correcting kernel)
-__host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt, int dist_slots = 0)
+__host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt, int dist_slots = 0, bool lean = false)
 {
     WarpOffsets W;
     const size_t dist_bytes = align16((size_t)(dist_slots > N ? dist_slots : N) * 8),
@@ -39,6 +39,12 @@ __host__ __device__ inline WarpOffsets warp_offsets(int N, bool alias_cnt, int d
     size_t o = dist_bytes;
     W.pk = o;   o += align16((size_t)N * 2);
     W.q0 = o;   o += align16((size_t)N * 2);
+    if (lean) {
+        // hierarchy sweeps + packed subtree words (warp_aon_chain): one queue (the leaves) is all the origin needs
+        W.q1 = W.q0; W.cnt = W.q0; W.mask = W.q0; W.tail = W.q0;
+        W.total = o;
+        return W;
+    }
     W.q1 = o;   o += align16((size_t)N * 2);
     if (alias_cnt && align16((size_t)N * 4) + cnt_bytes <= dist_bytes) W.cnt = align16((size_t)N * 4);
     else { W.cnt = o; o += cnt_bytes; }
@@ -54,7 +60,7 @@ struct SmemLayout {
 
 // cch_w_bytes: contraction-hierarchy weights kept in shared memory (0 = none / label-correcting kernel)
 __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, int warps, int real_bytes, bool alias_cnt,
-                                                  int dist_slots = 0, size_t cch_w_bytes = 0)
+                                                  int dist_slots = 0, size_t cch_w_bytes = 0, bool lean = false)
 {
     SmemLayout L;
     size_t o = 0;
@@ -66,7 +72,7 @@ __host__ __device__ inline SmemLayout make_layout(int N, int E, int topo_bytes, 
     L.off_red = o;  o += align16((size_t)(kMaxWarps * 4 + 8) * 8);
     L.off_cchw = o; o += align16(cch_w_bytes);
     L.off_warp = o;
-    L.warp_stride = warp_offsets(N, alias_cnt, dist_slots).total;
+    L.warp_stride = warp_offsets(N, alias_cnt, dist_slots, lean).total;
     L.total = o + L.warp_stride * warps;
     return L;
 }
@@ -79,10 +85,10 @@ struct SmallOffsets {
 
 // contraction-hierarchy tables of the general fused kernel (b200_cch.cu), device pointers
 struct CchParams {
-    const uint32_t *dn_desc, *cz_init, *cz_desc, *cz_tab;
-    const uint16_t *dn_node, *dn_tail, *uo_ptr, *uo_head, *parent;
+    const uint32_t *dn_rows, *up_rows, *up_off, *cz_init, *cz_desc, *cz_tab;
+    const uint8_t *dn_flags, *up_flags;
     double *ws;            // per-CTA weight workspace in HBM (the part of W outside shared memory)
-    int F, wd, wu, slots, dn_batches, cz_rows;
+    int F, wd, wu, slots, dn_nrows, cz_rows;
     int wmode;             // 0: W in HBM/L2, 1: down region in shared memory, 2: all of W in shared memory
     int ws_stride;         // doubles per CTA in ws
     unsigned exact_hi;     // high word of the exactness bound (labels >= it trigger the Bellman-Ford fallback)
@@ -99,6 +105,7 @@ struct Params {
     int alias32, alias64;  // general kernel: counters aliased into dist[] (per precision; see warp_offsets)
     int warm;  // general kernel: warm-start shortest paths from the previous iteration's trees
     int intq;  // general kernel: all demands are integers (total < 2^31) -> exact int32 link loads
+    int kahn_pack;  // general kernel: integer demands < 2^28 per origin and out-degree <= 15 -> packed subtree words
     const int32_t *topo, *row, *origins, *od_ptr, *od_dst;
     const float *t0_csc, *cap0_csc, *t0, *cap0;
     const void *od_q;  // REAL

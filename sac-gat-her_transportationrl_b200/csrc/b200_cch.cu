@@ -8,11 +8,13 @@
 // ("lower triangle" (u,v),(v,x)).  Per (scenario, iteration) the CTA first CUSTOMIZES the weights
 // of the filled edges, W(u,x) = min(cost(u,x), min over lower triangles W(u,v) + W(v,x)); then the
 // distances from one origin are
-//   up phase    walk the origin's ancestors in the elimination tree, relax their edges to
-//               higher-ranked heads (a few dozen nodes), and
+//   up phase    the nodes the origin reaches through edges to higher-ranked heads (on a two-way network
+//               its ancestors in the elimination tree, a few dozen nodes), each relaxing those edges, and
 //   down sweep  ONE pass over all nodes by decreasing rank, each pulling from its higher-ranked
 //               in-neighbours - a static schedule: nodes of one level are independent, their in-edges
-//               are stored as ELL rows (32 destinations x degree) in exactly the order the sweep reads.
+//               are ELL rows (32 destinations x degree) of packed words "tail slot | weight position",
+//               a read-only table shared by every origin of every scenario (it lives in L1); the weights
+//               themselves are stored compactly (one per filled edge) in shared memory.
 // Every filled edge is relaxed once per origin (Anaheim-size: 1 272 for 914 links; Chicago-Sketch-size:
 // 10 224 for 2 950) instead of the ~7 relaxations per link of frontier label correcting.
 //
@@ -38,7 +40,7 @@ namespace {
 
 struct Plan {
     int N = 0, F = 0;
-    std::vector<int> rank, order, parent;
+    std::vector<int> rank, order;
     std::vector<std::pair<int, int>> edges;                 // filled directed edges (tail, head)
     std::vector<int> orig_slot;                             // CSC slot of the original link or -1
     std::vector<std::vector<std::pair<int, int>>> tris;     // per edge: (edge (u,v), edge (v,x))
@@ -69,7 +71,6 @@ Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
         for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k) add_edge(in_src[k], v, k);
     (void)E;
     P.rank.assign(N, -1);
-    P.parent.assign(N, N);
     std::vector<char> alive(N, 1);
     int remaining = N;
     std::vector<int> cand;
@@ -107,22 +108,30 @@ Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
                     }
         }
     }
-    // elimination-tree parent = lowest-ranked higher neighbour (either direction)
-    for (size_t e = 0; e < P.edges.size(); ++e) {
-        int u = P.edges[e].first, x = P.edges[e].second;
-        int lo = P.rank[u] < P.rank[x] ? u : x, hi = lo == u ? x : u;
-        if (P.parent[lo] == N || P.rank[hi] < P.rank[P.parent[lo]]) P.parent[lo] = hi;
-    }
     P.F = (int)P.edges.size();
     return P;
 }
 
+// Row streams: what a warp executes is a sequence of ROWS of 32 words (one per lane) with one flag byte
+// per row, read strictly in order - so the words are prefetched through a register ring, whatever the
+// latency of the level of the memory hierarchy they come from.
+//   down stream (shared by all origins): per batch a HEADER row (destination slot per lane, bit 16 set for a
+//   partial slot, which starts from +inf instead of its old content; kRowSync: a warp barrier first, the
+//   batch starts a new level) followed by its edge rows "tail slot | weight
+//   position << 16" (padding: +inf slot | zero-weight position); the last edge row carries kRowLast
+//   (store the destination).
+//   up stream (one per origin): per elimination-tree ancestor with out-edges to higher ranks a HEADER row
+//   (the ancestor, same word in every lane) followed by rows of "head | up-region position << 16"
+//   (padding: +inf slot | the +inf weight).
+// Streams are padded to a multiple of 8 rows with inert edge rows (flag 0).
+enum { kRowHeader = 1, kRowSync = 2, kRowLast = 4 };
+
 struct DownLayout {
-    std::vector<uint32_t> desc;     // per batch: in-degree | 0x10000 if a warp barrier must precede it
-    std::vector<uint16_t> node;     // per batch 32 destination slots
-    std::vector<uint16_t> tail;     // ELL tails
+    std::vector<uint32_t> rows;     // [n_rows][32]
+    std::vector<uint8_t> flags;     // [n_rows]
     std::vector<int> edge_pos;      // W position of every down edge (by edge id), -1 otherwise
-    int slots = 0, wlen = 0;
+    int slots = 0, wlen = 0;        // wlen: down-region positions = the down edges, compact, then ONE zero-weight slot
+    int batches = 0;
     long cost = 0;
 };
 
@@ -162,8 +171,10 @@ DownLayout down_layout(const Plan &P)
     for (int v = 0; v < N; ++v)
         if (!dn[v].empty()) by_level[level[v]].push_back(v);
     std::vector<Item> items;
-    int next_slot = N + 1;   // slot N = +inf
+    int max_slot = N + 1;   // slot N = +inf; partial slots follow and are reused from level to level (a partial
+                            // is dead once its node has combined, and a warp barrier separates the levels)
     for (int l = 1; l <= max_level; ++l) {
+        int next_slot = N + 1;
         const std::vector<int> &nodes = by_level[l];
         int maxd = 0;
         for (int v : nodes) maxd = std::max(maxd, (int)dn[v].size());
@@ -201,36 +212,48 @@ DownLayout down_layout(const Plan &P)
                 items.push_back(std::move(it));
             }
         }
+        max_slot = std::max(max_slot, next_slot);
     }
-    D.slots = next_slot;
+    D.slots = max_slot;
+    int n_down = 0;
+    for (int v = 0; v < N; ++v) n_down += (int)dn[v].size();
+    const uint32_t ZERO = (uint32_t)n_down;   // zero-weight position: padding and partial-combine entries
+    D.wlen = n_down + 1;
+    int next_pos = 0;
     std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
         return a.key != b.key ? a.key < b.key : a.in.size() > b.in.size();
     });
     int prev_key = -1;
+    const uint32_t pad = (uint32_t)N | (ZERO << 16);   // tail = the +inf slot, weight 0
     for (size_t i = 0; i < items.size();) {
         size_t j = i;
         while (j < items.size() && j - i < 32 && items[j].key == items[i].key) ++j;
         const int deg = (int)items[i].in.size();
-        D.desc.push_back((uint32_t)deg | (items[i].key != prev_key && prev_key >= 0 ? 0x10000u : 0u));
+        const bool sync = items[i].key != prev_key && prev_key >= 0;
         prev_key = items[i].key;
-        const int base = (int)D.tail.size();
-        D.tail.resize(base + deg * 32, (uint16_t)N);   // padding: tail = the +inf slot, weight 0
-        for (int l = 0; l < 32; ++l) {
-            if (i + l < j) {
-                const Item &it = items[i + l];
-                D.node.push_back((uint16_t)it.dest);
-                for (int t = 0; t < (int)it.in.size(); ++t) {
-                    D.tail[base + t * 32 + l] = (uint16_t)it.in[t].first;
-                    if (it.in[t].second >= 0) D.edge_pos[it.in[t].second] = base + t * 32 + l;
-                }
-            } else {
-                D.node.push_back((uint16_t)N);   // idle lane: min(+inf, +inf + 0) back into the +inf slot
+        D.flags.push_back((uint8_t)(kRowHeader | (sync ? kRowSync : 0)));
+        for (int l = 0; l < 32; ++l)   // idle lane: min(+inf, +inf + 0) back into the +inf slot; bit 16: a partial slot
+            D.rows.push_back(i + l < j ? (uint32_t)items[i + l].dest | (items[i + l].dest > N ? 0x10000u : 0u)   // starts from +inf (reused)
+                                       : (uint32_t)N);
+        const size_t base = D.rows.size();
+        D.rows.resize(base + (size_t)deg * 32, pad);
+        for (int t = 0; t < deg; ++t) D.flags.push_back((uint8_t)(t == deg - 1 ? kRowLast : 0));
+        for (int l = 0; l < 32 && i + l < j; ++l) {
+            const Item &it = items[i + l];
+            for (int t = 0; t < (int)it.in.size(); ++t) {
+                uint32_t wp = ZERO;
+                if (it.in[t].second >= 0) wp = (uint32_t)(D.edge_pos[it.in[t].second] = next_pos++);
+                D.rows[base + (size_t)t * 32 + l] = (uint32_t)it.in[t].first | (wp << 16);
             }
         }
-        D.cost += 10 + 9 * deg + ((D.desc.back() & 0x10000u) ? 3 : 0);
+        D.cost += 10 + 9 * deg + (sync ? 3 : 0);
+        ++D.batches;
         i = j;
     }
-    D.wlen = (int)D.tail.size();
+    while (D.flags.size() % 8) {
+        D.flags.push_back(0);
+        D.rows.resize(D.rows.size() + 32, pad);
+    }
     return D;
 }
 
@@ -246,13 +269,13 @@ int up(T **dst, const std::vector<T> &src)
 // Everything the kernel reads, as host vectors (uploaded by b200_cch_prepare, replayed on the host by
 // b200_cch_host_sssp).
 struct Tables {
-    std::vector<uint32_t> dn_desc, cz_init, cz_desc, cz_tab;
-    std::vector<uint16_t> dn_node, dn_tail, uo_ptr, uo_head, parent;
-    int F = 0, wd = 0, wu = 0, slots = 0, tris = 0;
+    std::vector<uint32_t> dn_rows, up_rows, up_off, cz_init, cz_desc, cz_tab;   // up_off[O + 1]: first row of origin slot s
+    std::vector<uint8_t> dn_flags, up_flags;
+    int F = 0, wd = 0, wu = 0, slots = 0, tris = 0, dn_batches = 0;
 };
 
 // false: the network is outside the 16-bit limits of the tables
-bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, Tables &T)
+bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, int O, const int32_t *origins, Tables &T)
 {
     if (N >= 65000 || E >= 65000) return false;
     Plan P = make_plan(N, E, in_ptr, in_src);
@@ -266,15 +289,55 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, Ta
     for (int v = 0; v < N; ++v) nu += (int)uo[v].size();
     const long wtot = (long)D.wlen + nu;
     if (wtot + 2 >= 65535 || D.slots >= 65535) return false;
-    T.uo_ptr.assign(N + 1, 0);
-    for (int v = 0; v < N; ++v) {
-        T.uo_ptr[v] = (uint16_t)T.uo_head.size();
-        for (int e : uo[v]) {
-            pos[e] = D.wlen + (int)T.uo_head.size();
-            T.uo_head.push_back((uint16_t)P.edges[e].second);
+    // up-region positions: out-edges to higher-ranked heads, grouped by tail
+    std::vector<int> uo_first(N + 1, 0);
+    {
+        int next = 0;
+        for (int v = 0; v < N; ++v) {
+            uo_first[v] = next;
+            for (int e : uo[v]) pos[e] = D.wlen + next++;
+        }
+        uo_first[N] = next;
+    }
+    // one up stream per origin: the nodes it reaches through edges to higher ranks, in rising rank, each
+    // pushing along its own edges to higher ranks.  (On a two-way network these are the origin's ancestors
+    // in the elimination tree; with one-way links the directed fill is sparser than the undirected one the
+    // tree is defined on, so the set is taken from the directed edges themselves.)
+    const uint32_t up_pad = (uint32_t)N | ((uint32_t)nu << 16);   // +inf slot | the +inf weight (first slot after the up region)
+    T.up_off.assign(O + 1, 0);
+    std::vector<char> seen(N, 0);
+    for (int s = 0; s < O; ++s) {
+        T.up_off[s] = (uint32_t)T.up_flags.size();
+        std::vector<int> reach{origins[s]}, stack{origins[s]};
+        seen[origins[s]] = 1;
+        while (!stack.empty()) {
+            const int a = stack.back();
+            stack.pop_back();
+            for (int e : uo[a]) {
+                const int x = P.edges[e].second;
+                if (!seen[x]) { seen[x] = 1; reach.push_back(x); stack.push_back(x); }
+            }
+        }
+        std::sort(reach.begin(), reach.end(), [&](int a, int b) { return P.rank[a] < P.rank[b]; });
+        for (int a : reach) {
+            seen[a] = 0;
+            const int d = (int)uo[a].size();
+            if (d == 0) continue;
+            T.up_flags.push_back((uint8_t)kRowHeader);
+            T.up_rows.insert(T.up_rows.end(), 32, (uint32_t)a);
+            for (int r = 0; r < d; r += 32) {
+                T.up_flags.push_back(0);
+                for (int l = 0; l < 32; ++l)
+                    T.up_rows.push_back(r + l < d ? (uint32_t)P.edges[uo[a][r + l]].second | ((uint32_t)(uo_first[a] + r + l) << 16)
+                                                  : up_pad);
+            }
+        }
+        while (T.up_flags.size() % 8) {
+            T.up_flags.push_back(0);
+            T.up_rows.insert(T.up_rows.end(), 32, up_pad);
         }
     }
-    T.uo_ptr[N] = (uint16_t)T.uo_head.size();
+    T.up_off[O] = (uint32_t)T.up_flags.size();
     for (int e = 0; e < P.F; ++e)
         if (D.edge_pos[e] >= 0) pos[e] = D.edge_pos[e];
     const uint32_t INFPOS = (uint32_t)wtot, DUMMY = (uint32_t)wtot + 1;
@@ -315,12 +378,9 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, Ta
                 }
         }
     }
-    T.parent.resize(N);
-    for (int v = 0; v < N; ++v) T.parent[v] = (uint16_t)P.parent[v];
-    T.dn_desc = std::move(D.desc);
-    T.dn_node = std::move(D.node);
-    T.dn_tail = std::move(D.tail);
-    T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots;
+    T.dn_rows = std::move(D.rows);
+    T.dn_flags = std::move(D.flags);
+    T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots; T.dn_batches = D.batches;
     return true;
 }
 
@@ -349,9 +409,10 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
     std::vector<int32_t> in_ptr, in_src, in_eid;
     make_csc(N, E, row, col, in_ptr, in_src, in_eid);
     Tables T;
-    if (!build_tables(N, E, in_ptr.data(), in_src.data(), T)) { b200_set_error("network too large for the hierarchy tables"); return B200_EUNSUPPORTED; }
+    const int32_t one_origin[1] = {origin};
+    if (!build_tables(N, E, in_ptr.data(), in_src.data(), 1, one_origin, T)) { b200_set_error("network too large for the hierarchy tables"); return B200_EUNSUPPORTED; }
     const double INF = INFINITY;
-    std::vector<double> W((size_t)T.wd + T.wu + 2, 0.0);
+    std::vector<double> W((size_t)T.wd + T.wu + 2, 0.0);   // position wd - 1 keeps 0.0: the zero-weight slot
     W[T.wd + T.wu] = INF;
     for (int e = 0; e < T.F; ++e) {
         const uint32_t wi = T.cz_init[e];
@@ -374,29 +435,39 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
     }
     std::vector<double> d(T.slots, INF);
     d[origin] = 0.0;
-    for (int a = origin; a < N; a = T.parent[a])
-        for (int j = T.uo_ptr[a]; j < T.uo_ptr[a + 1]; ++j) {
-            const double c = d[a] + W[T.wd + j];
-            if (c < d[T.uo_head[j]]) d[T.uo_head[j]] = c;
-        }
-    off = 0;
-    for (size_t b = 0; b < T.dn_desc.size(); ++b) {
-        const int deg = (int)(T.dn_desc[b] & 0xffffu);
-        double best[32];
-        for (int l = 0; l < 32; ++l) {
-            best[l] = d[T.dn_node[b * 32 + l]];
-            for (int j = 0; j < deg; ++j) {
-                const double c = d[T.dn_tail[off + j * 32 + l]] + W[off + j * 32 + l];
-                if (c < best[l]) best[l] = c;
+    {   // up stream of this origin
+        double da = INF;
+        for (uint32_t r = T.up_off[0]; r < T.up_off[1]; ++r) {
+            const uint32_t *row = &T.up_rows[(size_t)r * 32];
+            if (T.up_flags[r] & kRowHeader) { da = d[row[0] & 0xffffu]; continue; }
+            for (int l = 0; l < 32; ++l) {
+                const double c = da + W[T.wd + (row[l] >> 16)];
+                if (c < d[row[l] & 0xffffu]) d[row[l] & 0xffffu] = c;
             }
         }
-        for (int l = 0; l < 32; ++l) d[T.dn_node[b * 32 + l]] = best[l];
-        off += (size_t)deg * 32;
+    }
+    {   // down stream
+        int dest[32];
+        double best[32];
+        for (int l = 0; l < 32; ++l) { dest[l] = N; best[l] = INF; }
+        for (size_t r = 0; r < T.dn_flags.size(); ++r) {
+            const uint32_t *row = &T.dn_rows[r * 32];
+            if (T.dn_flags[r] & kRowHeader) {
+                for (int l = 0; l < 32; ++l) { dest[l] = (int)(row[l] & 0xffffu); best[l] = (row[l] & 0x10000u) ? INF : d[dest[l]]; }
+                continue;
+            }
+            for (int l = 0; l < 32; ++l) {
+                const double c = d[row[l] & 0xffffu] + W[row[l] >> 16];
+                if (c < best[l]) best[l] = c;
+            }
+            if (T.dn_flags[r] & kRowLast)
+                for (int l = 0; l < 32; ++l) d[dest[l]] = best[l];
+        }
     }
     for (int v = 0; v < N; ++v) dist_out[v] = d[v];
     if (stats) {
         stats[0] = T.F; stats[1] = T.tris; stats[2] = T.wd; stats[3] = T.wu; stats[4] = T.slots;
-        stats[5] = (int64_t)T.dn_desc.size(); stats[6] = (int64_t)T.cz_desc.size(); stats[7] = 0;
+        stats[5] = (int64_t)T.dn_batches; stats[6] = (int64_t)T.cz_desc.size(); stats[7] = (int64_t)T.dn_flags.size();
     }
     return 0;
 }
@@ -407,17 +478,18 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
 {
     g->cch_ok = 0;
     Tables T;
-    if (!build_tables(g->N, g->E, in_ptr, in_src, T)) return 0;
+    if (!build_tables(g->N, g->E, in_ptr, in_src, g->O, g->origins_host, T)) return 0;
     int rc;
-    if ((rc = up(&g->cch_dn_desc, T.dn_desc)) || (rc = up(&g->cch_dn_node, T.dn_node)) || (rc = up(&g->cch_dn_tail, T.dn_tail)) ||
-        (rc = up(&g->cch_uo_ptr, T.uo_ptr)) || (rc = up(&g->cch_uo_head, T.uo_head)) || (rc = up(&g->cch_parent, T.parent)) ||
+    if ((rc = up(&g->cch_dn_rows, T.dn_rows)) || (rc = up(&g->cch_dn_flags, T.dn_flags)) || (rc = up(&g->cch_up_rows, T.up_rows)) ||
+        (rc = up(&g->cch_up_flags, T.up_flags)) || (rc = up(&g->cch_up_off, T.up_off)) ||
         (rc = up(&g->cch_cz_init, T.cz_init)) || (rc = up(&g->cch_cz_desc, T.cz_desc)) || (rc = up(&g->cch_cz_tab, T.cz_tab)))
         return rc;
+    g->cch_dn_nrows = (int)T.dn_flags.size();
     g->cch_F = T.F;
     g->cch_wd = T.wd;
     g->cch_wu = T.wu;
     g->cch_slots = T.slots;
-    g->cch_dn_batches = (int)T.dn_desc.size();
+    g->cch_dn_batches = T.dn_batches;
     g->cch_cz_rows = (int)T.cz_desc.size();
     g->cch_tris = T.tris;
     int e2 = 0;
@@ -429,7 +501,7 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
 
 void b200_cch_destroy(b200_graph *g)
 {
-    void *ptrs[] = {g->cch_dn_desc, g->cch_dn_node, g->cch_dn_tail, g->cch_uo_ptr, g->cch_uo_head, g->cch_parent,
+    void *ptrs[] = {g->cch_dn_rows, g->cch_dn_flags, g->cch_up_rows, g->cch_up_flags, g->cch_up_off,
                     g->cch_cz_init, g->cch_cz_desc, g->cch_cz_tab, g->cch_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);

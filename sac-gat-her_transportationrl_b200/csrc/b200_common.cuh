@@ -54,6 +54,7 @@ struct b200_graph {
     // appended for the general fused kernel: out-link CSR (out_ptr[N+1] | out_dst[E]), same blob so
     // one TMA copy stages everything; gen_intq = all demands are integers (total < 2^31)
     int off_out_ptr, off_out_dst, gen_intq;
+    int kahn_pack;   // integer demands < 2^28 per origin, out-degree <= 15: packed subtree words (warp_aon_chain)
     // 16-bit copy of the whole blob for the general assignment kernels (half the shared memory);
     // offsets in uint16 elements, every array padded to 16 bytes
     uint16_t *topo16;
@@ -97,16 +98,17 @@ struct b200_graph {
     void *plugin_launch;   // launcher of the on-demand plugin that matched this topology (else built-in)
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32;
-    // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): down-sweep batches
-    // (descriptor, 32 destination slots, ELL tails), up-phase CSR (out-edges to higher-ranked heads) and
-    // elimination-tree parents, customization tables (initial weight per filled edge, rows of 32 edges
-    // with their lower triangles); W positions: [0, cch_wd) down region, then cch_wu up-region entries,
+    // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): the down row stream
+    // (rows of 32 words + one flag byte per row), one up row stream per origin (up_off[O + 1]),
+    // customization tables (initial weight per filled edge, rows of 32 edges
+    // with their lower triangles); W positions: [0, cch_wd) down edges + one zero-weight slot, then cch_wu up-region entries,
     // then the +inf and the write-only dummy slot.  cch_ws: per-CTA weight workspace in HBM for the
     // part of W that does not fit shared memory, grown on demand like tree_ws.
     int cch_ok, cch_F, cch_wd, cch_wu, cch_slots, cch_dn_batches, cch_cz_rows, cch_tris, cch_wmode;
     double cch_exact_limit;
-    uint32_t *cch_dn_desc, *cch_cz_init, *cch_cz_desc, *cch_cz_tab;
-    uint16_t *cch_dn_node, *cch_dn_tail, *cch_uo_ptr, *cch_uo_head, *cch_parent;
+    uint32_t *cch_dn_rows, *cch_up_rows, *cch_up_off, *cch_cz_init, *cch_cz_desc, *cch_cz_tab;
+    uint8_t *cch_dn_flags, *cch_up_flags;
+    int cch_dn_nrows;
     double *cch_ws;
     size_t cch_ws_bytes, smem_cch;
     int warps_cch;

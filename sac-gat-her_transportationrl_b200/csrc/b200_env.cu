@@ -170,6 +170,117 @@ __global__ void __launch_bounds__(kFeatWarps * 32) features_kernel(FeatParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// reset(): damage sampling on the device (reference :167-190)
+// ---------------------------------------------------------------------------------------------
+// One warp per scenario.  A try = `count` distinct links by a partial Fisher-Yates shuffle (lane 0, on
+// a shared-memory permutation, randoms from a counter-based 64-bit mixer), accepted when the undamaged
+// links form a strongly connected subgraph on the nodes they touch - forward and backward reachability
+// from the lowest such node, relaxed by the whole warp to a fixed point.  Like the reference: at most
+// max_tries tries, then one more draw kept unconditionally.  The random stream is not numpy's (the
+// reference draws with Generator.choice); the RULE and the distribution are the reference's.
+struct SampleParams {
+    int N, E, B, count, max_tries;
+    const int32_t *topo;  // in_ptr | in_src | in_eid
+    int off_in_src, off_in_eid;
+    const int32_t *out_ptr, *out_dst, *out_eid;
+    unsigned long long seed;
+    unsigned long long *counters;
+    const uint8_t *select;
+    uint8_t *dmg;
+    int32_t *tries;
+};
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z += 0x9e3779b97f4a7c15ull;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+constexpr int kSampleWarps = 4;
+
+__global__ void __launch_bounds__(kSampleWarps * 32) sample_damage_kernel(SampleParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = p.N, E = p.E, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kSampleWarps + warp;
+    if (b >= p.B) return;
+    if (p.select && !p.select[b]) return;
+    const int32_t *in_ptr = p.topo, *in_src = p.topo + p.off_in_src, *in_eid = p.topo + p.off_in_eid;
+    const size_t stride = (size_t)((E * 2 + 15) & ~15) + (size_t)((E + 15) & ~15) + 2 * (size_t)((N + 15) & ~15);
+    unsigned char *wb = smem + stride * warp;
+    uint16_t *perm = (uint16_t *)wb;
+    uint8_t *dmg = wb + ((E * 2 + 15) & ~15);
+    uint8_t *fwd = dmg + ((E + 15) & ~15), *bwd = fwd + ((N + 15) & ~15);
+    const unsigned FULL = 0xffffffffu;
+    unsigned long long ctr = p.counters[b];
+    const unsigned long long key = p.seed ^ (0xd1342543de82ef95ull * (unsigned long long)(b + 1));
+    int tries = 0;
+    for (;; ++tries) {
+        for (int e = lane; e < E; e += 32) { perm[e] = (uint16_t)e; dmg[e] = 0; }
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < p.count; ++i) {
+                const unsigned long long r = mix64(key + mix64(ctr + (unsigned long long)i));
+                const int j = i + (int)__umul64hi(r, (unsigned long long)(E - i));
+                const uint16_t t = perm[i]; perm[i] = perm[j]; perm[j] = t;
+                dmg[perm[i]] = 1;
+            }
+        }
+        ctr += (unsigned long long)p.count;
+        __syncwarp();
+        if (tries >= p.max_tries) break;   // the reference's unconstrained last draw
+        // nodes of the edge-induced subgraph of undamaged links; its lowest node is the root
+        int root = N;
+        for (int v = lane; v < N; v += 32) {
+            bool present = false;
+            for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k) present |= dmg[in_eid[k]] == 0;
+            for (int k = __ldg(p.out_ptr + v); k < __ldg(p.out_ptr + v + 1); ++k) present |= dmg[__ldg(p.out_eid + k)] == 0;
+            fwd[v] = present ? 0 : 2;   // 2 = not part of the subgraph
+            bwd[v] = present ? 0 : 2;
+            if (present && v < root) root = v;
+        }
+        root = __reduce_min_sync(FULL, root);
+        __syncwarp();
+        bool ok = root < N;
+        if (ok) {
+            if (lane == 0) { fwd[root] = 1; bwd[root] = 1; }
+            __syncwarp();
+            for (bool changed = true; changed;) {
+                changed = false;
+                for (int v = lane; v < N; v += 32) {
+                    if (fwd[v] == 0) {
+                        bool hit = false;
+                        for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k) hit |= dmg[in_eid[k]] == 0 && fwd[in_src[k]] == 1;
+                        if (hit) { fwd[v] = 1; changed = true; }
+                    }
+                    if (bwd[v] == 0) {
+                        bool hit = false;
+                        for (int k = __ldg(p.out_ptr + v); k < __ldg(p.out_ptr + v + 1); ++k)
+                            hit |= dmg[__ldg(p.out_eid + k)] == 0 && bwd[__ldg(p.out_dst + k)] == 1;
+                        if (hit) { bwd[v] = 1; changed = true; }
+                    }
+                }
+                __syncwarp();
+                changed = __any_sync(FULL, changed);
+            }
+            bool all = true;
+            for (int v = lane; v < N; v += 32) all &= fwd[v] != 0 && bwd[v] != 0;
+            ok = __all_sync(FULL, all);
+        }
+        if (ok) break;
+    }
+    uint8_t *out = p.dmg + (size_t)b * E;
+    for (int e = lane; e < E; e += 32) out[e] = dmg[e];
+    if (lane == 0) {
+        p.counters[b] = ctr;
+        if (p.tries) p.tries[b] = tries + 1;
+    }
+}
+
+
 __global__ void apply_actions_kernel(int B, int E, const int32_t *action, uint8_t *dmg, uint8_t *valid, int32_t *status)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -274,6 +385,27 @@ extern "C" int b200_reward_done(const b200_graph *g, int B, int reward_mode, con
     reward_done_kernel<<<(B + per_block - 1) / per_block, threads, 0, (cudaStream_t)stream>>>(
         B, g->E, reward_mode, prev_tstt, tstt, initial_tstt, dmg, goal, valid, r_alpha, r_beta, r_gamma, r_clip, reward,
         done);
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200_sample_damage(const b200_graph *g, int B, int count, int max_tries, uint64_t seed, uint64_t *counters,
+                                  const uint8_t *select, uint8_t *dmg, int32_t *tries, void *stream)
+{
+    B200_REQUIRE(g && counters && dmg && B >= 0, "bad argument");
+    B200_REQUIRE(count >= 1 && count <= g->E && max_tries >= 0, "need 1 <= count <= E, max_tries >= 0");
+    B200_REQUIRE(g->E < 65536, "network too large for the 16-bit permutation");
+    if (B == 0) return 0;
+    SampleParams p;
+    p.N = g->N; p.E = g->E; p.B = B; p.count = count; p.max_tries = max_tries;
+    p.topo = g->topo; p.off_in_src = g->off_in_src; p.off_in_eid = g->off_in_eid;
+    p.out_ptr = g->out_ptr; p.out_dst = g->out_dst; p.out_eid = g->out_eid;
+    p.seed = seed; p.counters = (unsigned long long *)counters; p.select = select; p.dmg = dmg; p.tries = tries;
+    const size_t stride = (size_t)((g->E * 2 + 15) & ~15) + (size_t)((g->E + 15) & ~15) + 2 * (size_t)((g->N + 15) & ~15);
+    const size_t smem = stride * kSampleWarps;
+    B200_REQUIRE(smem <= 200 * 1024, "network too large for the sampler's shared-memory scratch");
+    B200_CUDA(cudaFuncSetAttribute(sample_damage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sample_damage_kernel<<<(B + kSampleWarps - 1) / kSampleWarps, kSampleWarps * 32, smem, (cudaStream_t)stream>>>(p);
     B200_CUDA(cudaGetLastError());
     return 0;
 }

@@ -157,6 +157,16 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
         bool intq = total < 2147483648.0;
         for (int k = 0; k < num_od && intq; ++k) intq = od_q[k] >= 0.0 && od_q[k] == floor(od_q[k]);
         g->gen_intq = intq ? 1 : 0;
+        // packed Kahn words of the general kernel: 4 bits of pending children, 28 bits of subtree demand
+        int max_out = 0;
+        for (int v = 0; v < N; ++v) max_out = std::max(max_out, out_ptr[v + 1] - out_ptr[v]);
+        double max_origin = 0.0;
+        for (int s2 = 0; s2 < O; ++s2) {
+            double t = 0.0;
+            for (int j = od_ptr[s2]; j < od_ptr[s2 + 1]; ++j) t += q64[j];
+            max_origin = std::max(max_origin, t);
+        }
+        g->kahn_pack = (intq && max_out <= 15 && max_origin < 268435456.0 && !getenv("B200_NO_KAHN_PACK")) ? 1 : 0;
     }
     int rc;
     if ((rc = upload(&g->topo, blob))) return rc;

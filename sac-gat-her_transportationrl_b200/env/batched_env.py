@@ -191,7 +191,8 @@ class BatchedRepairEnv:
                  reward_beta: float = 10.0, reward_gamma: float = 0.1, reward_clip: float = 0.0,
                  capacity_damage: float = 1e-3, unassigned_penalty: float = 2e7, fixed_damage: bool = False,
                  fixed_damage_seed: Optional[int] = None, seed: int = 0, seeds: Optional[Sequence[int]] = None,
-                 line_search_iters: int = 24, specialize_kernel: bool = False):
+                 line_search_iters: int = 24, specialize_kernel: bool = False, device_sampling: bool = False,
+                 sampler_seed: Optional[int] = None):
         if assignment_iters <= 0:
             raise ValueError("assignment_iters must be > 0 to update TSTT.")
         self.assignment_method = assignment_method.lower()
@@ -218,9 +219,15 @@ class BatchedRepairEnv:
         if len(seeds) != self.B:
             raise ValueError("need one seed per environment")
         self.rngs = [np.random.default_rng(s) for s in seeds]
-        self._fixed_rngs = ([np.random.default_rng(fixed_damage_seed + b) for b in range(self.B)]
-                            if fixed_damage_seed is not None else None)
+        # fixed_damage, as in the reference (:79-81, :171-190; src/train.py:160-161 gives every rollout worker
+        # the same fixed_damage_seed): with a seed, ONE scenario - the first draw of default_rng(seed) - shared
+        # by every env of every rank; without one, every env keeps the first draw of its OWN generator
+        # (`seeds`, which the trainer offsets by rank, so ranks do not duplicate each other).
+        self.fixed_damage_seed = fixed_damage_seed
         self._fixed_damage = None
+        self._fixed_damage_dev = None
+        self.device_sampling = bool(device_sampling)
+        self._sampler_seed = int(seeds[0]) * 0x9E3779B1 + 0x5851F42D if sampler_seed is None else int(sampler_seed)
         dev, real = self.device, self.engine.real
         self.is_damaged = torch.zeros((self.B, self.E), dtype=torch.uint8, device=dev)
         self.goal_mask = torch.zeros((self.B, self.E), dtype=torch.uint8, device=dev)
@@ -238,6 +245,8 @@ class BatchedRepairEnv:
         self._done = torch.zeros((self.B,), dtype=torch.uint8, device=dev)
         self._act_status = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self._pinned_mask = torch.zeros((self.B, self.E), dtype=torch.uint8).pin_memory()
+        self._sampler_counters = torch.zeros((self.B,), dtype=torch.int64, device=dev)   # device random-stream positions
+        self._sampler_tries = torch.zeros((self.B,), dtype=torch.int32, device=dev)
         self.edge_index = torch.from_numpy(self.network.edge_index).to(dev)
         self.assignments_done = 0
 
@@ -265,25 +274,46 @@ class BatchedRepairEnv:
 
     # ---- reset / step -------------------------------------------------------------------------
     def sample_damage_masks(self, damaged_ratio: float) -> np.ndarray:
+        """Host draw with the reference's generator and retry rule (one numpy Generator per env): what makes
+        env b reproduce ``RepairEnv(seed=seeds[b])`` draw for draw."""
         if self.fixed_damage and self._fixed_damage is not None:
             return self._fixed_damage
         masks = np.zeros((self.B, self.E), dtype=np.uint8)
-        for b in range(self.B):
-            rng = self._fixed_rngs[b] if (self.fixed_damage and self._fixed_rngs is not None) else self.rngs[b]
-            masks[b, self.network.sample_damage(rng, damaged_ratio)] = 1
+        if self.fixed_damage and self.fixed_damage_seed is not None:
+            masks[:, self.network.sample_damage(np.random.default_rng(self.fixed_damage_seed), damaged_ratio)] = 1
+        else:
+            for b in range(self.B):
+                masks[b, self.network.sample_damage(self.rngs[b], damaged_ratio)] = 1
         if self.fixed_damage:
             self._fixed_damage = masks
         return masks
 
+    def sample_damage_device(self, damaged_ratio: float, select: Optional[torch.Tensor] = None) -> None:
+        """Redraw ``is_damaged`` of the rows with ``select[b]`` (all rows when None) ON THE DEVICE
+        (``b200_sample_damage``: same rule as the reference - <= 50 tries for a strongly connected
+        undamaged subgraph, then an unconstrained draw - from a counter-based random stream, not numpy's).
+        No host synchronisation; used at episode boundaries of a lock-step batch."""
+        count = max(1, int(self.E * damaged_ratio))
+        eng = self.engine
+        if select is not None:
+            select = select.to(device=self.device, dtype=torch.uint8).contiguous()
+        _native.check(eng.lib.b200_sample_damage(
+            eng.h, self.B, count, 50, self._sampler_seed & 0xFFFFFFFFFFFFFFFF, _ptr(self._sampler_counters), _ptr(select),
+            _ptr(self.is_damaged), _ptr(self._sampler_tries), eng._stream()), "b200_sample_damage")
+        eng.launches += 1
+
     def reset(self, damaged_ratio: Optional[float] = None, damage_masks=None) -> BatchedEnvState:
         ratio = self.damaged_ratio if damaged_ratio is None else damaged_ratio
-        if damage_masks is None:
-            damage_masks = self.sample_damage_masks(ratio)
-        if isinstance(damage_masks, np.ndarray):
-            self._pinned_mask.copy_(torch.from_numpy(np.ascontiguousarray(damage_masks, dtype=np.uint8)))
-            self.is_damaged.copy_(self._pinned_mask, non_blocking=True)
+        if damage_masks is None and self.device_sampling and not self.fixed_damage:
+            self.sample_damage_device(ratio)
         else:
-            self.is_damaged.copy_(damage_masks.to(torch.uint8))
+            if damage_masks is None:
+                damage_masks = self.sample_damage_masks(ratio)
+            if isinstance(damage_masks, np.ndarray):
+                self._pinned_mask.copy_(torch.from_numpy(np.ascontiguousarray(damage_masks, dtype=np.uint8)))
+                self.is_damaged.copy_(self._pinned_mask, non_blocking=True)
+            else:
+                self.is_damaged.copy_(damage_masks.to(torch.uint8))
         self.goal_mask.copy_(self.is_damaged)
         self.flow.zero_()  # cold start (reference :198, :302-303)
         self.compute_flow_assignment()
@@ -292,27 +322,23 @@ class BatchedRepairEnv:
 
     def reset_where(self, mask: torch.Tensor, damaged_ratio: Optional[float] = None) -> None:
         """Per-scenario reset (episode boundaries in a lock-step batch): scenarios with ``mask[b]``
-        get a fresh damage draw (their own generator; the cached draw under ``fixed_damage``),
-        zero flows, goal := damage, a cold-start assignment and a new ``initial_tstt``; the
-        others are untouched.  The reference resets one env at a time (:167-205)."""
+        get a fresh damage draw (the cached draw under ``fixed_damage``, otherwise the device sampler),
+        zero flows, goal := damage, a cold-start assignment and a new ``initial_tstt``; the others are
+        untouched.  Everything stays on the device: no host synchronisation, no per-env Python loop (the
+        reference resets one env at a time, :167-205)."""
         mask = mask.to(device=self.device, dtype=torch.bool)
-        idx = torch.nonzero(mask, as_tuple=False).squeeze(1)
-        if idx.numel() == 0:
-            return
         ratio = self.damaged_ratio if damaged_ratio is None else damaged_ratio
-        rows = idx.cpu().tolist()
+        sel = mask.to(torch.uint8)
         if self.fixed_damage:
-            new = torch.from_numpy(self.sample_damage_masks(ratio)[rows])
+            if self._fixed_damage_dev is None:
+                self._fixed_damage_dev = torch.from_numpy(self.sample_damage_masks(ratio)).to(self.device)
+            self.is_damaged.copy_(torch.where(mask.unsqueeze(1), self._fixed_damage_dev, self.is_damaged))
         else:
-            host = np.zeros((len(rows), self.E), dtype=np.uint8)
-            for i, b in enumerate(rows):
-                host[i, self.network.sample_damage(self.rngs[b], ratio)] = 1
-            new = torch.from_numpy(host)
-        self.is_damaged[idx] = new.to(self.device)
-        self.goal_mask[idx] = self.is_damaged[idx]
-        self.flow[idx] = 0
-        self.compute_flow_assignment(active=mask.to(torch.uint8))
-        self.initial_tstt[idx] = self.tstt[idx]
+            self.sample_damage_device(ratio, sel)
+        self.goal_mask.copy_(torch.where(mask.unsqueeze(1), self.is_damaged, self.goal_mask))
+        self.flow.mul_((~mask).unsqueeze(1).to(self.flow.dtype))
+        self.compute_flow_assignment(active=sel)
+        self.initial_tstt.copy_(torch.where(mask, self.tstt, self.initial_tstt))
 
     def compute_flow_assignment(self, active: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.engine.assign(self.is_damaged, self.flow, self.assignment_iters, self.assignment_method, self._out,

@@ -212,10 +212,17 @@ class DiscreteSAC:
                     "critic2": self.critic2.state_dict(), "target1": self.target1.state_dict(),
                     "target2": self.target2.state_dict(), "log_alpha": self.log_alpha.detach().cpu()}, path)
 
-    def load(self, path: str, map_location="cpu", strict: bool = True) -> None:
+    def load(self, path: str, map_location="cpu", strict: bool = True) -> Dict[str, Dict[str, list]]:
+        """Load a checkpoint in the reference's file layout (src/rl/sac.py:278-287).  ``strict=False``
+        accepts checkpoints of older revisions of the reference (the shipped
+        ``history-data/outputs1/model_best.pt`` predates the input / per-layer LayerNorms): returns, per
+        module, the keys the checkpoint did not provide (``missing``) and the ones it had in excess
+        (``unexpected``) so the caller can assert what was consumed."""
         state = torch.load(path, map_location=map_location, weights_only=True)
-        self.actor.load_state_dict(state["actor"], strict=strict)
-        for name in ("critic1", "critic2", "target1", "target2"):
-            getattr(self, name).load_state_dict(state[name], strict=strict)
+        report = {}
+        for name in ("actor", "critic1", "critic2", "target1", "target2"):
+            res = getattr(self, name).load_state_dict(state[name], strict=strict)
+            report[name] = {"missing": list(res.missing_keys), "unexpected": list(res.unexpected_keys)}
         with torch.no_grad():
             self.log_alpha.copy_(state["log_alpha"].to(self.device))
+        return report

@@ -57,3 +57,25 @@ def test_hierarchy_handles_unreachable_nodes_and_one_way_links(b200env, native_l
         ref, _, _ = orc.sssp(cost, [o])
         dist, _ = _host_sssp(native_lib, orc, cost, o)
         assert np.array_equal(dist, ref[0]), o
+
+
+def test_hierarchy_on_random_digraphs_with_one_way_links(b200env, native_lib):
+    """One-way links make the directed fill sparser than the undirected one: the up phase must follow the
+    directed edges to higher ranks, not the elimination tree (regression: a 70-node network with a one-way
+    chain gave labels that were too long)."""
+    from oracle.c_oracle import COracle
+    E = b200env.EdgeData
+    for seed, n, extra in ((8, 70, 60), (1, 40, 90), (2, 120, 100), (3, 25, 200)):
+        rng = np.random.default_rng(seed)
+        links = {(i, i + 1) for i in range(1, n - 1)} | {(i + 1, i) for i in range(1, n - 1) if i % 3}
+        links |= {(int(a), int(b)) for a, b in rng.integers(1, n, size=(extra, 2)) if a != b}
+        links = sorted(links)
+        g = b200env.GraphData(num_nodes=n, edges=[E(u, v, 900.0, float(1 + (u * 7 + v) % 5), float(1 + (u * 7 + v) % 5), 0.15, 4.0)
+                                                   for u, v in links], od_demand={(1, 2): 1.0})
+        orc = COracle.from_graph_data(g)
+        cost = orc.t0.astype(np.float64)
+        cost[rng.choice(orc.E, orc.E // 5, replace=False)] = 1e6
+        ref, _, _ = orc.sssp(cost, np.arange(n, dtype=np.int32))
+        for o in range(n):
+            dist, _ = _host_sssp(native_lib, orc, cost, o)
+            assert np.array_equal(dist, ref[o]), (seed, o)
