@@ -46,6 +46,7 @@ struct Cta {
     double *wd, *wu;
     int cch_wd;
     bool lean;   // per-warp scratch without the second queue / counters (warp_offsets)
+    int topo_bytes;   // staged part of the topology blob
 
     // link load of link e as REAL, whatever the accumulation type
     __device__ __forceinline__ REAL auxv(int e) const { return intq ? (REAL)((const int *)aux)[e] : aux[e]; }
@@ -55,7 +56,8 @@ struct Cta {
         alias_cnt = (sizeof(REAL) == 4 ? p.alias32 : p.alias64) != 0;
         const int wmode = cch ? p.cch.wmode : 0;
         const size_t w_smem = !cch ? 0 : (wmode == 2 ? (size_t)(p.cch.wd + p.cch.wu + 2) * 8 : wmode == 1 ? (size_t)p.cch.wd * 8 : 0);
-        SmemLayout L = make_layout(p.N, p.E, p.topo16_bytes, warps, (int)sizeof(REAL), alias_cnt, cch ? p.cch.slots : 0,
+        topo_bytes = cch ? p.cch.topo_bytes : p.topo16_bytes;
+        SmemLayout L = make_layout(p.N, p.E, topo_bytes, warps, (int)sizeof(REAL), alias_cnt, cch ? p.cch.slots : 0,
                                    w_smem, cch && p.kahn_pack);
         lean = cch && p.kahn_pack;
         if (cch) {
@@ -94,7 +96,7 @@ struct Cta {
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t bytes = (uint32_t)p.topo16_bytes;
+            const uint32_t bytes = (uint32_t)topo_bytes;
             mbar_expect_tx(bar, bytes);
             tma_bulk_g2s(topo, p.topo16, bytes, bar);
         }
@@ -373,10 +375,11 @@ __device__ void cta_customize(const Cta<REAL> &c, const Params &p)
 // labels leave the exactly-summable range (never on the shipped networks; B200_CCH_LIMIT forces it
 // in the tests).
 template <typename REAL>
-__device__ int warp_sssp_bf(const Cta<REAL> &c, int origin, const WarpScratch &s)
+__device__ int warp_sssp_bf(const Cta<REAL> &c, const Params &p, int origin, const WarpScratch &s)
 {
     const int lane = threadIdx.x & 31, N = c.N;
     double *dist = s.dist;
+    const int32_t *in_ptr = p.topo, *in_src = p.topo + p.off_in_src;   // the 32-bit blob in HBM: this path is cold
     for (int v = lane; v < N; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     __syncwarp();
     for (int round = 0; round <= N; ++round) {
@@ -384,8 +387,8 @@ __device__ int warp_sssp_bf(const Cta<REAL> &c, int origin, const WarpScratch &s
         for (int v = lane; v < N; v += 32) {
             const double dv = dist[v];
             double best = dv;
-            for (int k = c.in_ptr[v]; k < c.in_ptr[v + 1]; ++k) {
-                const double cand = dist[c.in_src[k]] + c.w[k];
+            for (int k = __ldg(in_ptr + v); k < __ldg(in_ptr + v + 1); ++k) {
+                const double cand = dist[__ldg(in_src + k)] + c.w[k];
                 best = cand < best ? cand : best;
             }
             if (best < dv) { dist[v] = best; changed = true; }
@@ -396,36 +399,41 @@ __device__ int warp_sssp_bf(const Cta<REAL> &c, int origin, const WarpScratch &s
     return 1;
 }
 
-// Row-stream engine: calls f(word, flag) for every row of a stream ([nrows][32] words, one flag byte per
-// row, nrows a multiple of 8; see b200_cch.cu).  The rows are read strictly in order, so each lane keeps
-// the next 8 words of its column in registers: by the time a row is processed its load was issued 8 rows
-// earlier, which hides L1, L2 and HBM latency alike - the tables need not fit shared memory.
-template <class F>
-__device__ __forceinline__ void stream_rows(const uint32_t *__restrict__ rows, const uint8_t *__restrict__ flags, int nrows,
-                                            F &&f)
+// Down stream of the hierarchy (b200_cch.cu): batches of a header row + D edge rows, all of one shape, so
+// the loop body is branch-free; the words of the NEXT batch are fetched into registers before the current
+// one is relaxed, which hides the latency of whatever level of the memory hierarchy holds the table.
+template <int D>
+__device__ __forceinline__ void cch_down_sweep(const uint32_t *__restrict__ rows, int batches, double *dist,
+                                               const double *__restrict__ wd)
 {
-    if (nrows <= 0) return;
+    if (batches <= 0) return;
     const uint32_t *rp = rows + (threadIdx.x & 31);
-    uint32_t ring[8];
+    uint32_t cur[D + 1], nxt[D + 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) ring[i] = __ldg(rp + i * 32);
-    uint2 fl = __ldg((const uint2 *)flags);
-    for (int s = 0; s < nrows; s += 8) {
-        const bool more = s + 8 < nrows;
-        const uint2 fnext = more ? __ldg((const uint2 *)(flags + s + 8)) : make_uint2(0u, 0u);
-        rp += 256;
+    for (int i = 0; i <= D; ++i) cur[i] = __ldg(rp + i * 32);
+    for (int b = 0; b < batches; ++b) {
+        rp += (D + 1) * 32;
+        if (b + 1 < batches) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t e = ring[i];
-            if (more) ring[i] = __ldg(rp + i * 32);
-            f(e, ((i < 4 ? fl.x : fl.y) >> (8 * (i & 3))) & 0xffu);
+            for (int i = 0; i <= D; ++i) nxt[i] = __ldg(rp + i * 32);
         }
-        fl = fnext;
+        __syncwarp();   // the labels this batch pulls from (earlier levels / stages) are complete
+        double *dst = dist + (cur[0] & 0xffffu);
+        double best = (cur[0] & 0x10000u) ? B200_INF_F64 : *dst;   // partial slots are reused from level to level
+        double cand[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) cand[i] = dist[cur[i + 1] & 0xffffu] + wd[cur[i + 1] >> 16];
+#pragma unroll
+        for (int i = 0; i < D; ++i) best = cand[i] < best ? cand[i] : best;
+        *dst = best;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) cur[i] = nxt[i];
     }
 }
 
-// One warp, one origin: up stream of the origin (its elimination-tree ancestors push along their edges to
-// higher ranks), then the down stream shared by all origins (b200_cch.cu); labels are exact sums, checked below.
+// One warp, one origin: up stream of the origin (the nodes it reaches through edges to higher ranks push
+// along those edges, in rising rank), then the down stream shared by all origins; labels are exact sums,
+// checked below.
 template <typename REAL>
 __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int origin, const WarpScratch &s)
 {
@@ -435,35 +443,29 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
     for (int v = lane; v < h.slots; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     {
         const double *__restrict__ wu = c.wu;
-        const uint32_t r0 = __ldg(h.up_off + slot), r1 = __ldg(h.up_off + slot + 1);
-        double da = B200_INF_F64;
-        stream_rows(h.up_rows + (size_t)r0 * 32, h.up_flags + r0, (int)(r1 - r0), [&](uint32_t e, uint32_t fb) {
-            if (fb & 1u) {   // next ancestor: every lower one has pushed, its label is final
-                __syncwarp();
-                da = dist[e & 0xffffu];
-            } else {
-                const double cand = da + wu[e >> 16];
-                double *dx = dist + (e & 0xffffu);
-                if (cand < *dx) *dx = cand;
-            }
-        });
+        const int q0 = (int)__ldg(h.up_off + slot), q1 = (int)__ldg(h.up_off + slot + 1);
+        const uint32_t *rp = h.up_rows + (size_t)q0 * 64 + lane;
+        uint32_t a = 0, e = 0;
+        if (q0 < q1) { a = __ldg(rp); e = __ldg(rp + 32); }
+        for (int q = q0; q < q1; ++q) {
+            rp += 64;
+            uint32_t an = 0, en = 0;
+            if (q + 1 < q1) { an = __ldg(rp); en = __ldg(rp + 32); }
+            __syncwarp();   // every lower node has pushed: the label of this one is final
+            const double cand = dist[a & 0xffffu] + wu[e >> 16];
+            double *dx = dist + (e & 0xffffu);
+            if (cand < *dx) *dx = cand;
+            a = an; e = en;
+        }
     }
-    __syncwarp();   // initial labels and the last pushes are visible to the whole warp
-    {
-        const double *__restrict__ wd = c.wd;
-        int dest = N;
-        double best = B200_INF_F64;
-        stream_rows(h.dn_rows, h.dn_flags, h.dn_nrows, [&](uint32_t e, uint32_t fb) {
-            if (fb & 1u) {   // header: destination slots of the next batch
-                if (fb & 2u) __syncwarp();   // first batch of a level: the labels it pulls from are complete
-                dest = (int)(e & 0xffffu);
-                best = (e & 0x10000u) ? B200_INF_F64 : dist[dest];   // partial slots are reused from level to level
-            } else {
-                const double cand = dist[e & 0xffffu] + wd[e >> 16];
-                best = cand < best ? cand : best;
-                if (fb & 4u) dist[dest] = best;
-            }
-        });
+    __syncwarp();
+    switch (h.D) {
+        case 2: cch_down_sweep<2>(h.dn_rows, h.dn_batches, dist, c.wd); break;
+        case 3: cch_down_sweep<3>(h.dn_rows, h.dn_batches, dist, c.wd); break;
+        case 4: cch_down_sweep<4>(h.dn_rows, h.dn_batches, dist, c.wd); break;
+        case 5: cch_down_sweep<5>(h.dn_rows, h.dn_batches, dist, c.wd); break;
+        case 6: cch_down_sweep<6>(h.dn_rows, h.dn_batches, dist, c.wd); break;
+        default: cch_down_sweep<8>(h.dn_rows, h.dn_batches, dist, c.wd); break;
     }
     __syncwarp();
     unsigned mx = 0;
@@ -472,8 +474,26 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
         mx = hi < 0x7ff00000u && hi > mx ? hi : mx;
     }
     int capped = 0;
-    if (__reduce_max_sync(0xffffffffu, mx) >= h.exact_hi) capped = warp_sssp_bf<REAL>(c, origin, s);
-    warp_select_pred<REAL>(c, origin, s);
+    if (__reduce_max_sync(0xffffffffu, mx) >= h.exact_hi) capped = warp_sssp_bf<REAL>(c, p, origin, s);
+    // predecessor: tight in-link with the smallest dist[u], then the largest u - from the select stream (rows of
+    // "tail | CSC slot" per block of 32 nodes, ascending tail, so "<=" leaves the largest u among equals)
+    const double *__restrict__ w = c.w;
+    const uint32_t *sp = h.sel_rows + lane;
+    for (int v = lane; v < ((N + 31) & ~31); v += 32, sp += h.SD * 32) {
+        const double dv = v < N ? dist[v] : B200_INF_F64;
+        int bk = kNoPk;
+        double bdu = B200_INF_F64;
+#pragma unroll 4
+        for (int j = 0; j < h.SD; ++j) {
+            const uint32_t e = __ldg(sp + j * 32);
+            const double du = dist[e & 0xffffu];
+            const bool take = du + w[e >> 16] == dv && du <= bdu;
+            bk = take ? (int)(e >> 16) : bk;
+            bdu = take ? du : bdu;
+        }
+        if (v < N) s.pk[v] = (uint16_t)((v != origin && dv < B200_INF_F64) ? bk : kNoPk);
+    }
+    __syncwarp();
     return capped;
 }
 
@@ -1043,11 +1063,13 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     p.st_origpos = g->st_origpos;
     p.total_demand = g->total_demand;
     if (g->cch_ok) {
-        p.cch.dn_rows = g->cch_dn_rows; p.cch.dn_flags = g->cch_dn_flags; p.cch.up_rows = g->cch_up_rows;
-        p.cch.up_flags = g->cch_up_flags; p.cch.up_off = g->cch_up_off; p.cch.cz_init = g->cch_cz_init;
+        p.cch.dn_rows = g->cch_dn_rows; p.cch.up_rows = g->cch_up_rows; p.cch.sel_rows = g->cch_sel_rows;
+        p.cch.up_off = g->cch_up_off; p.cch.cz_init = g->cch_cz_init;
         p.cch.cz_desc = g->cch_cz_desc; p.cch.cz_tab = g->cch_cz_tab;
         p.cch.F = g->cch_F; p.cch.wd = g->cch_wd; p.cch.wu = g->cch_wu; p.cch.slots = g->cch_slots;
-        p.cch.dn_nrows = g->cch_dn_nrows; p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
+        p.cch.dn_batches = g->cch_dn_batches; p.cch.D = g->cch_D; p.cch.SD = g->cch_SD;
+        p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
+        p.cch.topo_bytes = g->o16_out_ptr * 2;   // in_ptr | in_src | in_eid: the out-link arrays are not needed
         union { double d; unsigned long long u; } lim;
         lim.d = g->cch_exact_limit;
         p.cch.exact_hi = (unsigned)(lim.u >> 32);
@@ -1189,7 +1211,7 @@ int b200_pick_warps_cch(b200_graph *g)
         if (forced_m >= 0 && mode != forced_m) continue;
         const size_t wb = mode == 2 ? (size_t)(g->cch_wd + g->cch_wu + 2) * 8 : mode == 1 ? (size_t)g->cch_wd * 8 : 0;
         for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-            SmemLayout L = make_layout(g->N, g->E, g->topo16_bytes, w, 4, true, g->cch_slots, wb, g->kahn_pack != 0);
+            SmemLayout L = make_layout(g->N, g->E, g->o16_out_ptr * 2, w, 4, true, g->cch_slots, wb, g->kahn_pack != 0);
             if (L.total > kSmemLimit) break;
             if (forced_w && w != forced_w) continue;
             const int O = std::max(g->O, 1);
@@ -1197,7 +1219,7 @@ int b200_pick_warps_cch(b200_graph *g)
             const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
             // resident warps, with a premium for weights in shared memory: every origin gathers from the whole
             // down region, and the up phase is a chain of dependent reads (L2 latency per ancestor otherwise)
-            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 2.0 : mode == 1 ? 1.6 : 1.0);
+            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 1.3 : mode == 1 ? 1.15 : 1.0);
             if (score > best_score + 1e-9) { best_score = score; best_w = w; best_m = mode; best_smem = L.total; }
         }
     }

@@ -112,149 +112,96 @@ Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
     return P;
 }
 
-// Row streams: what a warp executes is a sequence of ROWS of 32 words (one per lane) with one flag byte
-// per row, read strictly in order - so the words are prefetched through a register ring, whatever the
-// latency of the level of the memory hierarchy they come from.
-//   down stream (shared by all origins): per batch a HEADER row (destination slot per lane, bit 16 set for a
-//   partial slot, which starts from +inf instead of its old content; kRowSync: a warp barrier first, the
-//   batch starts a new level) followed by its edge rows "tail slot | weight
-//   position << 16" (padding: +inf slot | zero-weight position); the last edge row carries kRowLast
-//   (store the destination).
-//   up stream (one per origin): per elimination-tree ancestor with out-edges to higher ranks a HEADER row
-//   (the ancestor, same word in every lane) followed by rows of "head | up-region position << 16"
-//   (padding: +inf slot | the +inf weight).
-// Streams are padded to a multiple of 8 rows with inert edge rows (flag 0).
-enum { kRowHeader = 1, kRowSync = 2, kRowLast = 4 };
-
+// Row streams: what a warp executes is a sequence of ROWS of 32 words (one per lane), read strictly in
+// order and all of ONE fixed shape per stream, so the kernel's loops are branch-free, fully unrolled and
+// prefetch the next batch through registers whatever level of the memory hierarchy serves the table.
+//   down stream (shared by all origins): batches of 1 + D rows - a header row (destination slot per lane;
+//   bit 16: a partial slot, which starts from +inf instead of its old content) and exactly D edge rows
+//   "tail slot | weight position << 16" (padding: +inf slot | zero-weight position).  A warp barrier
+//   precedes every batch.  Destinations with more than D in-edges are split: chunks of D edges go to partial
+//   slots first, the node then combines its partials through zero-weight entries one stage later (again in
+//   chunks of D if need be).  D is chosen per network by the row count of the whole sweep.
+//   up stream (one per origin): pairs of rows - the pushing node (same word in every lane), then up to 32
+//   of its edges to higher ranks "head | up-region position << 16" (padding: +inf slot | the +inf weight).
+//   select stream (shared): for every block of 32 nodes SD rows "tail | CSC slot << 16" of their original
+//   in-links in ascending tail order (padding: +inf slot | slot 0), SD = largest in-degree.
 struct DownLayout {
-    std::vector<uint32_t> rows;     // [n_rows][32]
-    std::vector<uint8_t> flags;     // [n_rows]
+    std::vector<uint32_t> rows;     // [batches][1 + D][32]
     std::vector<int> edge_pos;      // W position of every down edge (by edge id), -1 otherwise
     int slots = 0, wlen = 0;        // wlen: down-region positions = the down edges, compact, then ONE zero-weight slot
-    int batches = 0;
-    long cost = 0;
+    int batches = 0, D = 0;
 };
 
-// Layout of the down sweep.  Nodes of one level are independent; a level with few, high-degree nodes
-// would leave most lanes idle, so per level the in-edges of a node may be split into chunks of c edges
-// that go to partial slots first (the node then combines its partials through zero-weight entries in a
-// sub-level of its own).  c is chosen per level by the instruction-count model of the sweep:
-// 10 + 9 x degree per batch of 32 destinations, 3 per barrier.
-struct Item { int key, dest; std::vector<std::pair<int, int>> in; };   // in: (tail slot, edge id or -1 = zero weight)
+struct Item { int level, stage, dest; std::vector<std::pair<int, int>> in; };   // in: (tail slot, edge id or -1 = zero weight)
 
-long batches_cost(std::vector<int> degs)
-{
-    std::sort(degs.begin(), degs.end(), std::greater<int>());
-    long cost = 0;
-    for (size_t i = 0; i < degs.size(); i += 32) cost += 10 + 9 * degs[i];
-    return cost;
-}
-
-DownLayout down_layout(const Plan &P)
+// Layout of the down sweep for edge rows per batch D (see above).
+DownLayout down_layout(const Plan &P, int D)
 {
     const int N = P.N;
-    DownLayout D;
-    D.edge_pos.assign(P.F, -1);
+    DownLayout L;
+    L.D = D;
+    L.edge_pos.assign(P.F, -1);
     std::vector<std::vector<int>> dn(N);   // down in-edges (edge ids) per head
+    int n_down = 0;
     for (int e = 0; e < P.F; ++e)
-        if (P.rank[P.edges[e].first] > P.rank[P.edges[e].second]) dn[P.edges[e].second].push_back(e);
+        if (P.rank[P.edges[e].first] > P.rank[P.edges[e].second]) { dn[P.edges[e].second].push_back(e); ++n_down; }
     std::vector<int> level(N, 0);
-    int max_level = 0;
     for (int r = N - 1; r >= 0; --r) {
         const int v = P.order[r];
         int l = 0;
         for (int e : dn[v]) l = std::max(l, level[P.edges[e].first] + 1);
         level[v] = l;
-        max_level = std::max(max_level, l);
     }
-    std::vector<std::vector<int>> by_level(max_level + 1);
-    for (int v = 0; v < N; ++v)
-        if (!dn[v].empty()) by_level[level[v]].push_back(v);
     std::vector<Item> items;
-    int max_slot = N + 1;   // slot N = +inf; partial slots follow and are reused from level to level (a partial
-                            // is dead once its node has combined, and a warp barrier separates the levels)
-    for (int l = 1; l <= max_level; ++l) {
-        int next_slot = N + 1;
-        const std::vector<int> &nodes = by_level[l];
-        int maxd = 0;
-        for (int v : nodes) maxd = std::max(maxd, (int)dn[v].size());
-        int best_c = maxd;
-        long best_cost = -1;
-        for (int c = 1; c <= maxd; ++c) {
-            std::vector<int> first, second;
-            for (int v : nodes) {
-                const int d = (int)dn[v].size();
-                if (d > c) {
-                    for (int i = 0; i < d; i += c) first.push_back(std::min(c, d - i));
-                    second.push_back((d + c - 1) / c);
-                } else {
-                    first.push_back(d);
-                }
+    std::map<int, int> next_slot;   // per level: partial slots are reused from level to level (a partial is dead
+    int max_slot = N + 1;           // once its node has combined, and barriers separate the levels); slot N = +inf
+    for (int v = 0; v < N; ++v) {
+        if (dn[v].empty()) continue;
+        std::vector<std::pair<int, int>> in;
+        for (int e : dn[v]) in.push_back({P.edges[e].first, e});
+        int stage = 0;
+        int &ns = next_slot.emplace(level[v], N + 1).first->second;
+        while ((int)in.size() > D) {
+            std::vector<std::pair<int, int>> up;
+            for (size_t i = 0; i < in.size(); i += D) {
+                Item part{level[v], stage, ns, {}};
+                part.in.assign(in.begin() + i, in.begin() + std::min(in.size(), i + D));
+                up.push_back({ns++, -1});
+                items.push_back(std::move(part));
             }
-            const long cost = batches_cost(first) + (second.empty() ? 0 : 3 + batches_cost(second));
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; }
+            in = std::move(up);
+            ++stage;
         }
-        for (int v : nodes) {
-            const int d = (int)dn[v].size();
-            if (d > best_c) {
-                Item comb{l * 2 + 1, v, {}};
-                for (int i = 0; i < d; i += best_c) {
-                    Item part{l * 2, next_slot, {}};
-                    for (int j = i; j < std::min(d, i + best_c); ++j) part.in.push_back({P.edges[dn[v][j]].first, dn[v][j]});
-                    comb.in.push_back({next_slot, -1});
-                    ++next_slot;
-                    items.push_back(std::move(part));
-                }
-                items.push_back(std::move(comb));
-            } else {
-                Item it{l * 2, v, {}};
-                for (int e : dn[v]) it.in.push_back({P.edges[e].first, e});
-                items.push_back(std::move(it));
-            }
-        }
-        max_slot = std::max(max_slot, next_slot);
+        max_slot = std::max(max_slot, ns);
+        items.push_back(Item{level[v], stage, v, std::move(in)});
     }
-    D.slots = max_slot;
-    int n_down = 0;
-    for (int v = 0; v < N; ++v) n_down += (int)dn[v].size();
+    L.slots = max_slot;
     const uint32_t ZERO = (uint32_t)n_down;   // zero-weight position: padding and partial-combine entries
-    D.wlen = n_down + 1;
+    L.wlen = n_down + 1;
     int next_pos = 0;
     std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-        return a.key != b.key ? a.key < b.key : a.in.size() > b.in.size();
+        return a.level != b.level ? a.level < b.level : a.stage < b.stage;
     });
-    int prev_key = -1;
     const uint32_t pad = (uint32_t)N | (ZERO << 16);   // tail = the +inf slot, weight 0
     for (size_t i = 0; i < items.size();) {
         size_t j = i;
-        while (j < items.size() && j - i < 32 && items[j].key == items[i].key) ++j;
-        const int deg = (int)items[i].in.size();
-        const bool sync = items[i].key != prev_key && prev_key >= 0;
-        prev_key = items[i].key;
-        D.flags.push_back((uint8_t)(kRowHeader | (sync ? kRowSync : 0)));
-        for (int l = 0; l < 32; ++l)   // idle lane: min(+inf, +inf + 0) back into the +inf slot; bit 16: a partial slot
-            D.rows.push_back(i + l < j ? (uint32_t)items[i + l].dest | (items[i + l].dest > N ? 0x10000u : 0u)   // starts from +inf (reused)
-                                       : (uint32_t)N);
-        const size_t base = D.rows.size();
-        D.rows.resize(base + (size_t)deg * 32, pad);
-        for (int t = 0; t < deg; ++t) D.flags.push_back((uint8_t)(t == deg - 1 ? kRowLast : 0));
+        while (j < items.size() && j - i < 32 && items[j].level == items[i].level && items[j].stage == items[i].stage) ++j;
+        for (int l = 0; l < 32; ++l)   // idle lane: min(+inf, +inf + 0) back into the +inf slot
+            L.rows.push_back(i + l < j ? (uint32_t)items[i + l].dest | (items[i + l].dest > N ? 0x10000u : 0u) : (uint32_t)N);
+        const size_t base = L.rows.size();
+        L.rows.resize(base + (size_t)D * 32, pad);
         for (int l = 0; l < 32 && i + l < j; ++l) {
             const Item &it = items[i + l];
             for (int t = 0; t < (int)it.in.size(); ++t) {
                 uint32_t wp = ZERO;
-                if (it.in[t].second >= 0) wp = (uint32_t)(D.edge_pos[it.in[t].second] = next_pos++);
-                D.rows[base + (size_t)t * 32 + l] = (uint32_t)it.in[t].first | (wp << 16);
+                if (it.in[t].second >= 0) wp = (uint32_t)(L.edge_pos[it.in[t].second] = next_pos++);
+                L.rows[base + (size_t)t * 32 + l] = (uint32_t)it.in[t].first | (wp << 16);
             }
         }
-        D.cost += 10 + 9 * deg + (sync ? 3 : 0);
-        ++D.batches;
+        ++L.batches;
         i = j;
     }
-    while (D.flags.size() % 8) {
-        D.flags.push_back(0);
-        D.rows.resize(D.rows.size() + 32, pad);
-    }
-    return D;
+    return L;
 }
 
 template <typename T>
@@ -269,9 +216,8 @@ int up(T **dst, const std::vector<T> &src)
 // Everything the kernel reads, as host vectors (uploaded by b200_cch_prepare, replayed on the host by
 // b200_cch_host_sssp).
 struct Tables {
-    std::vector<uint32_t> dn_rows, up_rows, up_off, cz_init, cz_desc, cz_tab;   // up_off[O + 1]: first row of origin slot s
-    std::vector<uint8_t> dn_flags, up_flags;
-    int F = 0, wd = 0, wu = 0, slots = 0, tris = 0, dn_batches = 0;
+    std::vector<uint32_t> dn_rows, up_rows, up_off, sel_rows, cz_init, cz_desc, cz_tab;   // up_off[O + 1]: first PAIR of origin slot s
+    int F = 0, wd = 0, wu = 0, slots = 0, tris = 0, dn_batches = 0, D = 0, SD = 0;
 };
 
 // false: the network is outside the 16-bit limits of the tables
@@ -279,7 +225,11 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
 {
     if (N >= 65000 || E >= 65000) return false;
     Plan P = make_plan(N, E, in_ptr, in_src);
-    DownLayout D = down_layout(P);
+    DownLayout D;
+    for (int d : {2, 3, 4, 5, 6, 8}) {   // fewest rows wins (a row costs the same whatever it holds)
+        DownLayout c = down_layout(P, d);
+        if (D.batches == 0 || c.batches * (1 + c.D) < D.batches * (1 + D.D)) D = std::move(c);
+    }
     // up region: out-edges to higher-ranked heads, CSR by tail
     std::vector<int> pos(P.F, -1);
     std::vector<std::vector<int>> uo(N);
@@ -307,7 +257,7 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
     T.up_off.assign(O + 1, 0);
     std::vector<char> seen(N, 0);
     for (int s = 0; s < O; ++s) {
-        T.up_off[s] = (uint32_t)T.up_flags.size();
+        T.up_off[s] = (uint32_t)(T.up_rows.size() / 64);
         std::vector<int> reach{origins[s]}, stack{origins[s]};
         seen[origins[s]] = 1;
         while (!stack.empty()) {
@@ -322,22 +272,22 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
         for (int a : reach) {
             seen[a] = 0;
             const int d = (int)uo[a].size();
-            if (d == 0) continue;
-            T.up_flags.push_back((uint8_t)kRowHeader);
-            T.up_rows.insert(T.up_rows.end(), 32, (uint32_t)a);
             for (int r = 0; r < d; r += 32) {
-                T.up_flags.push_back(0);
+                T.up_rows.insert(T.up_rows.end(), 32, (uint32_t)a);
                 for (int l = 0; l < 32; ++l)
                     T.up_rows.push_back(r + l < d ? (uint32_t)P.edges[uo[a][r + l]].second | ((uint32_t)(uo_first[a] + r + l) << 16)
                                                   : up_pad);
             }
         }
-        while (T.up_flags.size() % 8) {
-            T.up_flags.push_back(0);
-            T.up_rows.insert(T.up_rows.end(), 32, up_pad);
-        }
     }
-    T.up_off[O] = (uint32_t)T.up_flags.size();
+    T.up_off[O] = (uint32_t)(T.up_rows.size() / 64);
+    // select stream: original in-links per block of 32 nodes
+    T.SD = 1;
+    for (int v = 0; v < N; ++v) T.SD = std::max(T.SD, in_ptr[v + 1] - in_ptr[v]);
+    T.sel_rows.assign((size_t)((N + 31) / 32) * T.SD * 32, (uint32_t)N);
+    for (int v = 0; v < N; ++v)
+        for (int k = in_ptr[v]; k < in_ptr[v + 1]; ++k)
+            T.sel_rows[((size_t)(v / 32) * T.SD + (k - in_ptr[v])) * 32 + (v % 32)] = (uint32_t)in_src[k] | ((uint32_t)k << 16);
     for (int e = 0; e < P.F; ++e)
         if (D.edge_pos[e] >= 0) pos[e] = D.edge_pos[e];
     const uint32_t INFPOS = (uint32_t)wtot, DUMMY = (uint32_t)wtot + 1;
@@ -379,8 +329,7 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
         }
     }
     T.dn_rows = std::move(D.rows);
-    T.dn_flags = std::move(D.flags);
-    T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots; T.dn_batches = D.batches;
+    T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots; T.dn_batches = D.batches; T.D = D.D;
     return true;
 }
 
@@ -435,39 +384,31 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
     }
     std::vector<double> d(T.slots, INF);
     d[origin] = 0.0;
-    {   // up stream of this origin
-        double da = INF;
-        for (uint32_t r = T.up_off[0]; r < T.up_off[1]; ++r) {
-            const uint32_t *row = &T.up_rows[(size_t)r * 32];
-            if (T.up_flags[r] & kRowHeader) { da = d[row[0] & 0xffffu]; continue; }
-            for (int l = 0; l < 32; ++l) {
-                const double c = da + W[T.wd + (row[l] >> 16)];
-                if (c < d[row[l] & 0xffffu]) d[row[l] & 0xffffu] = c;
-            }
+    for (uint32_t q = T.up_off[0]; q < T.up_off[1]; ++q) {   // up stream of this origin: (node, edges) row pairs
+        const uint32_t *row = &T.up_rows[(size_t)q * 64];
+        const double da = d[row[0] & 0xffffu];
+        for (int l = 0; l < 32; ++l) {
+            const double c = da + W[T.wd + (row[32 + l] >> 16)];
+            if (c < d[row[32 + l] & 0xffffu]) d[row[32 + l] & 0xffffu] = c;
         }
     }
-    {   // down stream
-        int dest[32];
+    for (int b = 0; b < T.dn_batches; ++b) {   // down stream: header row + D edge rows per batch
+        const uint32_t *row = &T.dn_rows[(size_t)b * (1 + T.D) * 32];
         double best[32];
-        for (int l = 0; l < 32; ++l) { dest[l] = N; best[l] = INF; }
-        for (size_t r = 0; r < T.dn_flags.size(); ++r) {
-            const uint32_t *row = &T.dn_rows[r * 32];
-            if (T.dn_flags[r] & kRowHeader) {
-                for (int l = 0; l < 32; ++l) { dest[l] = (int)(row[l] & 0xffffu); best[l] = (row[l] & 0x10000u) ? INF : d[dest[l]]; }
-                continue;
-            }
-            for (int l = 0; l < 32; ++l) {
-                const double c = d[row[l] & 0xffffu] + W[row[l] >> 16];
+        for (int l = 0; l < 32; ++l) {
+            best[l] = (row[l] & 0x10000u) ? INF : d[row[l] & 0xffffu];
+            for (int j = 1; j <= T.D; ++j) {
+                const uint32_t w = row[j * 32 + l];
+                const double c = d[w & 0xffffu] + W[w >> 16];
                 if (c < best[l]) best[l] = c;
             }
-            if (T.dn_flags[r] & kRowLast)
-                for (int l = 0; l < 32; ++l) d[dest[l]] = best[l];
         }
+        for (int l = 0; l < 32; ++l) d[row[l] & 0xffffu] = best[l];
     }
     for (int v = 0; v < N; ++v) dist_out[v] = d[v];
     if (stats) {
         stats[0] = T.F; stats[1] = T.tris; stats[2] = T.wd; stats[3] = T.wu; stats[4] = T.slots;
-        stats[5] = (int64_t)T.dn_batches; stats[6] = (int64_t)T.cz_desc.size(); stats[7] = (int64_t)T.dn_flags.size();
+        stats[5] = (int64_t)T.dn_batches; stats[6] = (int64_t)T.cz_desc.size(); stats[7] = (int64_t)T.D;
     }
     return 0;
 }
@@ -480,11 +421,12 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
     Tables T;
     if (!build_tables(g->N, g->E, in_ptr, in_src, g->O, g->origins_host, T)) return 0;
     int rc;
-    if ((rc = up(&g->cch_dn_rows, T.dn_rows)) || (rc = up(&g->cch_dn_flags, T.dn_flags)) || (rc = up(&g->cch_up_rows, T.up_rows)) ||
-        (rc = up(&g->cch_up_flags, T.up_flags)) || (rc = up(&g->cch_up_off, T.up_off)) ||
+    if ((rc = up(&g->cch_dn_rows, T.dn_rows)) || (rc = up(&g->cch_up_rows, T.up_rows)) ||
+        (rc = up(&g->cch_sel_rows, T.sel_rows)) || (rc = up(&g->cch_up_off, T.up_off)) ||
         (rc = up(&g->cch_cz_init, T.cz_init)) || (rc = up(&g->cch_cz_desc, T.cz_desc)) || (rc = up(&g->cch_cz_tab, T.cz_tab)))
         return rc;
-    g->cch_dn_nrows = (int)T.dn_flags.size();
+    g->cch_D = T.D;
+    g->cch_SD = T.SD;
     g->cch_F = T.F;
     g->cch_wd = T.wd;
     g->cch_wu = T.wu;
@@ -501,7 +443,7 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
 
 void b200_cch_destroy(b200_graph *g)
 {
-    void *ptrs[] = {g->cch_dn_rows, g->cch_dn_flags, g->cch_up_rows, g->cch_up_flags, g->cch_up_off,
+    void *ptrs[] = {g->cch_dn_rows, g->cch_up_rows, g->cch_sel_rows, g->cch_up_off,
                     g->cch_cz_init, g->cch_cz_desc, g->cch_cz_tab, g->cch_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);

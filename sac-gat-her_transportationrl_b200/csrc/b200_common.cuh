@@ -99,16 +99,15 @@ struct b200_graph {
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32;
     // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): the down row stream
-    // (rows of 32 words + one flag byte per row), one up row stream per origin (up_off[O + 1]),
+    // (batches of 1 + D rows of 32 words), one up row stream per origin (row pairs, up_off[O + 1]), the select stream,
     // customization tables (initial weight per filled edge, rows of 32 edges
     // with their lower triangles); W positions: [0, cch_wd) down edges + one zero-weight slot, then cch_wu up-region entries,
     // then the +inf and the write-only dummy slot.  cch_ws: per-CTA weight workspace in HBM for the
     // part of W that does not fit shared memory, grown on demand like tree_ws.
     int cch_ok, cch_F, cch_wd, cch_wu, cch_slots, cch_dn_batches, cch_cz_rows, cch_tris, cch_wmode;
     double cch_exact_limit;
-    uint32_t *cch_dn_rows, *cch_up_rows, *cch_up_off, *cch_cz_init, *cch_cz_desc, *cch_cz_tab;
-    uint8_t *cch_dn_flags, *cch_up_flags;
-    int cch_dn_nrows;
+    uint32_t *cch_dn_rows, *cch_up_rows, *cch_sel_rows, *cch_up_off, *cch_cz_init, *cch_cz_desc, *cch_cz_tab;
+    int cch_D, cch_SD;   // edge rows per down batch, rows per block of the select stream
     double *cch_ws;
     size_t cch_ws_bytes, smem_cch;
     int warps_cch;

@@ -9,11 +9,13 @@ critics and a device replay.  Per env step, on every rank:
   1. one batched actor forward picks an action per scenario (no weight broadcast: the learner and
      the rollout share the module);
   2. ``env.step`` = one fused assignment launch + reward/done/feature kernels;
-  3. the step's transitions are all-gathered over NCCL into every rank's replay (identical
-     replay contents on all ranks, sampled with rank-specific generators);
+  3. the step's transitions are all-gathered over NCCL into every rank's replay; every rank samples with
+     its own generator, and the (index, TD error) pairs of all ranks are all-gathered and applied in rank
+     order, so replay contents AND priorities stay identical on all ranks;
   4. every ``update_every`` steps, ``updates_per_step`` learner updates with gradients averaged
      over ranks (NCCL all-reduce);
-  5. scenarios that are done (or hit ``max_steps``) are reset in place.
+  5. scenarios that are done (or hit ``max_steps``) are reset in place ON THE DEVICE (damage redraw by
+     ``b200_sample_damage``, cold-start assignment): no host synchronisation at episode boundaries.
 The config keys are the reference's YAML keys (configs/sioux_falls.yaml); ``num_envs`` is new.
 """
 from __future__ import annotations
@@ -64,7 +66,7 @@ class BatchedTrainer:
             reward_mode=c["reward_mode"], reward_alpha=c["reward_alpha"], reward_beta=c["reward_beta"],
             reward_gamma=c["reward_gamma"], reward_clip=c["reward_clip"], capacity_damage=c["capacity_damage"],
             unassigned_penalty=c["unassigned_penalty"], fixed_damage=c["fixed_damage"],
-            fixed_damage_seed=c["fixed_damage_seed"], seeds=seeds)
+            fixed_damage_seed=c["fixed_damage_seed"], seeds=seeds, sampler_seed=c["seed"] * 1000003 + self.rank)
         net = self.env.network
         torch.manual_seed(c["seed"])  # identical initial weights on every rank
         self.agent = DiscreteSAC(net, 4, 6, c["hidden_dim"], c["embed_dim"], num_layers=c["gat_layers"], lr=c["lr"],
@@ -81,6 +83,9 @@ class BatchedTrainer:
         self.global_steps = 0
         self.stats = dict(env_steps=0, assignments=B, updates=0, episodes=0, nccl_ms=0.0, wall_s=0.0,
                           episode_reward_sum=0.0, last_losses={})
+        # counters that would cost a host sync per step live on the device and are read in run()
+        self._dev_counts = torch.zeros(3, dtype=torch.float64, device=self.device)   # valid actions, episodes, reward sum
+        self._timed_events = []
 
     # reward of a relabelled goal, through the same kernel the env uses (reference :244-291)
     def _reward_fn(self, prev, nxt, init, next_mask, goal):
@@ -114,7 +119,7 @@ class BatchedTrainer:
         out = self.agent.select_action(st.node_features, st.edge_features, st.action_mask, generator=self.gen)
         actions = out.action.to(torch.int32)
         prev_tstt = env.tstt.clone()
-        nst, reward, done, info = env.step(actions)
+        nst, reward, done, info = env.step(actions, validate_actions=False)   # actions come from a masked categorical
         local = {
             "node_x": st.node_features, "edge_attr": st.edge_features, "action_mask": st.action_mask.to(torch.uint8),
             "next_node_x": nst.node_features, "next_edge_attr": nst.edge_features,
@@ -126,7 +131,7 @@ class BatchedTrainer:
         self.replay.add_batch(gathered)
         self.global_steps += 1
         self.stats["env_steps"] += env.num_envs * self.world
-        self.stats["assignments"] += int(info["valid"].sum()) * self.world  # invalid actions skip the assignment
+        self._dev_counts[0] += info["valid"].sum()  # invalid actions skip the assignment
         self.ep_steps += 1
         self.ep_reward += reward * c["reward_scale"]
         if self.replay.size > c["batch_start"] and self.global_steps % c["update_every"] == 0:
@@ -135,23 +140,25 @@ class BatchedTrainer:
                 batch, idx, w = self.replay.sample(bs, generator=self.gen)
                 batch = DeviceReplay.relabel_hindsight(batch, c["her_ratio"], self._reward_fn, c["reward_scale"], self.gen)
                 losses = self.agent.update(batch, weights=w, alpha_max=c["alpha_max"])
-                self.replay.update_priorities(idx, losses["td_errors"])
+                if self.world > 1:   # every rank applies every rank's updates, in rank order: priorities stay identical
+                    both = self._timed_collective(lambda: all_gather_transitions(
+                        {"idx": idx, "td": losses["td_errors"].float()}))
+                    self.replay.update_priorities(both["idx"], both["td"])
+                else:
+                    self.replay.update_priorities(idx, losses["td_errors"])
                 self.stats["updates"] += 1
                 self.stats["last_losses"] = losses
         finished = done | (self.ep_steps >= c["max_steps"]) if c["max_steps"] > 0 else done
-        n_fin = int(finished.sum())
-        if n_fin:
-            self.stats["episodes"] += n_fin * self.world
-            self.stats["episode_reward_sum"] += float(self.ep_reward[finished].sum())
-            env.reset_where(finished)
-            self.stats["assignments"] += n_fin * self.world
-            self.ep_steps[finished] = 0
-            self.ep_reward[finished] = 0
-            nst = env.get_state()
+        # episode boundaries without a host round trip: the reset is a masked device operation (a no-op when
+        # nothing finished) and the state features are recomputed for the batch
+        self._dev_counts[1] += finished.sum()
+        self._dev_counts[2] += (self.ep_reward * finished).sum()
+        env.reset_where(finished)
+        self.ep_steps.mul_(~finished)
+        self.ep_reward.mul_(~finished)
+        nst = env.get_state()
         self.state = nst
-        if self._pending_events:
-            torch.cuda.synchronize(self.device)
-            self.stats["nccl_ms"] += sum(s.elapsed_time(e) for s, e in self._pending_events)
+        self._timed_events.extend(self._pending_events)   # read in run(): no per-step synchronisation
 
     def run(self, env_steps: int) -> Dict:
         """``env_steps`` lock-step steps; returns throughput figures (whole job, all ranks)."""
@@ -163,6 +170,13 @@ class BatchedTrainer:
         torch.cuda.synchronize(self.device)
         wall = time.perf_counter() - t0
         self.stats["wall_s"] += wall
+        self.stats["nccl_ms"] += sum(s.elapsed_time(e) for s, e in self._timed_events)
+        self._timed_events = []
+        counts = self._dev_counts.tolist()
+        self._dev_counts.zero_()
+        self.stats["assignments"] += int(counts[0] + counts[1]) * self.world   # step assignments + episode resets
+        self.stats["episodes"] += int(counts[1]) * self.world
+        self.stats["episode_reward_sum"] += counts[2]
         d = {k: self.stats[k] - base[k] for k in ("env_steps", "assignments", "updates", "episodes", "nccl_ms")}
         losses = {k: float(v) for k, v in self.stats["last_losses"].items() if k != "td_errors"}
         return {"env_steps_per_s": d["env_steps"] / wall, "assignments_per_s": d["assignments"] / wall,

@@ -265,3 +265,92 @@ def test_state_features_large_networks_vs_oracle_betweenness(b200env, native_lib
             dmg[b].astype(np.float32), goal[b].astype(np.float32),
             np.arange(E, dtype=np.float32) / max(E - 1, 1)], axis=1)
         np.testing.assert_allclose(edge[b], exp_e, rtol=1e-4, atol=2e-6)
+
+
+def test_device_damage_sampler_rule_determinism_and_distribution(b200env, native_lib, sf_graph):
+    """`b200_sample_damage` (reset's damage draw on the device, reference :167-190): every row gets exactly
+    `count` damaged links; the undamaged links are strongly connected on the nodes they touch whenever the
+    sampler says it found such a draw within 50 tries; same seed + counters => same masks; `select` leaves
+    the other rows untouched; and the per-link damage frequencies agree with the host sampler (numpy
+    Generator + the reference's retry rule) - same rule, same distribution, different random stream."""
+    B = 4096
+    env = b200env.BatchedRepairEnv(sf_graph, B, device="cuda:0", assignment_iters=2, seeds=list(range(B)), sampler_seed=77)
+    net = env.network
+    env.sample_damage_device(0.3)
+    m1, tries = env.is_damaged.cpu().numpy().copy(), env._sampler_tries.cpu().numpy().copy()
+    assert np.all(m1.sum(axis=1) == 22) and m1.max() == 1
+    assert tries.min() >= 1 and np.median(tries) > 2          # ~13 % of the draws are accepted
+    for b in range(0, B, 64):
+        if tries[b] <= 50:
+            assert net.active_subgraph_strongly_connected(m1[b].astype(np.float32)), b
+    assert np.unique(m1, axis=0).shape[0] > B * 0.99          # the rows are different draws
+    # determinism: a twin env with the same sampler seed reproduces the stream
+    twin = b200env.BatchedRepairEnv(sf_graph, B, device="cuda:0", assignment_iters=2, seeds=list(range(B)), sampler_seed=77)
+    twin.sample_damage_device(0.3)
+    assert torch.equal(twin.is_damaged, env.is_damaged)
+    # select: only the chosen rows are redrawn, and their stream moves on
+    sel = torch.zeros(B, dtype=torch.uint8, device="cuda:0")
+    sel[::3] = 1
+    counters0 = env._sampler_counters.clone()
+    env.sample_damage_device(0.3, sel)
+    m2 = env.is_damaged.cpu().numpy()
+    keep = sel.cpu().numpy() == 0
+    assert np.array_equal(m2[keep], m1[keep]) and not np.array_equal(m2[~keep], m1[~keep])
+    assert torch.equal(env._sampler_counters[1::3], counters0[1::3]) and bool((env._sampler_counters[::3] > counters0[::3]).all())
+    # distribution: per-link damage frequency vs 3000 host draws of the reference rule
+    rng = np.random.default_rng(5)
+    host = np.zeros(76)
+    n_host = 3000
+    for _ in range(n_host):
+        host[net.sample_damage(rng, 0.3)] += 1
+    f_dev, f_host = m1.mean(axis=0), host / n_host
+    se = np.sqrt(f_host * (1 - f_host) * (1 / n_host + 1 / B))
+    assert np.abs(f_dev - f_host).max() < 5 * se.max(), (np.abs(f_dev - f_host).max(), se.max())
+    assert f_dev.std() > 0.01                                  # connectivity makes some links much rarer than others
+
+
+def test_reset_where_runs_on_the_device_and_fixed_damage_semantics(b200env, native_lib, sf_graph):
+    """`reset_where` redraws, reassigns and re-bases only the selected scenarios, without touching the others;
+    under `fixed_damage` with a seed every env of every rank shares ONE scenario (the reference's meaning,
+    :79-81 and src/train.py:160-161), without a seed every env keeps the first draw of its own generator."""
+    B = 64
+    env = b200env.BatchedRepairEnv(sf_graph, B, device="cuda:0", assignment_method="fw", assignment_iters=20,
+                                   seeds=list(range(300, 300 + B)))
+    env.reset()
+    for _ in range(2):
+        env.step(torch.argmax(env.is_damaged, dim=1).to(torch.int32))
+    before = {k: getattr(env, k).clone() for k in ("is_damaged", "goal_mask", "flow", "tstt", "initial_tstt")}
+    mask = torch.zeros(B, dtype=torch.bool, device="cuda:0")
+    mask[5::7] = True
+    env.reset_where(mask)
+    keep = ~mask
+    for k, v in before.items():
+        assert torch.equal(getattr(env, k)[keep], v[keep]), k
+    assert torch.all(env.is_damaged[mask].sum(dim=1) == 22) and torch.equal(env.goal_mask[mask], env.is_damaged[mask])
+    assert torch.equal(env.initial_tstt[mask], env.tstt[mask]) and not torch.equal(env.is_damaged[mask], before["is_damaged"][mask])
+    # the re-based scenarios carry a genuine cold-start assignment of their new damage
+    from oracle.c_oracle import COracle
+    orc = COracle.from_graph_data(sf_graph)
+    for b in torch.nonzero(mask).flatten().tolist()[:3]:
+        o = orc.assign(env.is_damaged[b].cpu().numpy(), None, 20, "fw")
+        assert env.tstt[b].item() == o["tstt"] and np.array_equal(env.flow[b].cpu().numpy(), o["flow"])
+    # fixed damage with a seed: one shared scenario, identical on "another rank" (different env seeds)
+    a = b200env.BatchedRepairEnv(sf_graph, 8, device="cuda:0", assignment_iters=2, fixed_damage=True, fixed_damage_seed=42,
+                                 seeds=list(range(8)))
+    b_ = b200env.BatchedRepairEnv(sf_graph, 8, device="cuda:0", assignment_iters=2, fixed_damage=True, fixed_damage_seed=42,
+                                  seeds=list(range(8, 16)))
+    a.reset(); b_.reset()
+    ref = b200env.RepairEnv(sf_graph, device="cuda:0", assignment_iters=2, fixed_damage=True, fixed_damage_seed=42, seed=0)
+    assert torch.equal(a.is_damaged, b_.is_damaged) and torch.all(a.is_damaged == a.is_damaged[0])
+    assert np.array_equal(a.is_damaged[0].cpu().numpy(), (ref.is_damaged > 0).astype(np.uint8))
+    a.step(torch.argmax(a.is_damaged, dim=1).to(torch.int32))
+    a.reset_where(torch.ones(8, dtype=torch.bool, device="cuda:0"))
+    assert torch.equal(a.is_damaged, b_.is_damaged)                      # the cached scenario again
+    # fixed damage without a seed: per-env first draws, different between envs and between "ranks"
+    c = b200env.BatchedRepairEnv(sf_graph, 8, device="cuda:0", assignment_iters=2, fixed_damage=True, seeds=list(range(8)))
+    d = b200env.BatchedRepairEnv(sf_graph, 8, device="cuda:0", assignment_iters=2, fixed_damage=True, seeds=list(range(8, 16)))
+    c.reset(); d.reset()
+    assert not torch.equal(c.is_damaged, d.is_damaged) and not torch.all(c.is_damaged == c.is_damaged[0])
+    first = c.is_damaged.clone()
+    c.reset()
+    assert torch.equal(c.is_damaged, first)
