@@ -133,3 +133,55 @@ def test_evaluate_policies_on_common_scenarios(b200env, native_lib, sf_graph):
     k = max(1, int(76 * 0.08))
     assert all(t["steps"] == k for t in table.values())            # masked policies always repair a damaged link
     assert table["greedy"]["tstt_auc"] <= table["first"]["tstt_auc"] * (1 + 1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+# the batched trainer on two NCCL ranks (BASELINE.json config 5; reference src/train.py:138-214, :730-913)
+# ---------------------------------------------------------------------------------------------
+def _nccl_trainer_worker(rank, world, port, out_dir):
+    import os
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, repo)
+    import torch.distributed as dist
+    import b200env
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        cfg = dict(num_envs=32, assignment_iters=8, assignment_method="cfw", batch_start=64, buffer_size=4096, batch_size=32,
+                   update_every=2, hidden_dim=16, embed_dim=16, fixed_damage=False, max_steps=6, seed=5)
+        tr = b200env.rl.BatchedTrainer(b200env.load_sioux_falls(), cfg, device=f"cuda:{rank}")
+        res = tr.run(12)
+        R = tr.replay
+        state = {"masks0": tr.env.is_damaged.cpu(), "size": R.size, "ptr": R.ptr,
+                 "store": {k: v[:R.size].cpu() for k, v in R.store.items()}, "priority": R.priority[:R.size].cpu(),
+                 "max_priority": R.max_priority, "updates": tr.stats["updates"],
+                 "actor": {k: v.cpu() for k, v in tr.agent.actor.state_dict().items()},
+                 "critic1": {k: v.cpu() for k, v in tr.agent.critic1.state_dict().items()},
+                 "log_alpha": tr.agent.log_alpha.detach().cpu(), "res": res}
+        torch.save(state, os.path.join(out_dir, f"rank{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run with gpurun --gpus 2)")
+def test_batched_trainer_two_nccl_ranks_stay_in_lock_step(native_lib, tmp_path):
+    """Two ranks, NCCL: the per-step transition all-gather gives both replays the same contents in the same
+    order, the all-gathered priority updates keep the priorities equal, the gradient all-reduce keeps the
+    weights equal after every update - while each rank rolls out its OWN scenarios (rank-offset seeds)."""
+    import torch.multiprocessing as mp
+    port = 29000 + (int(torch.randint(0, 2000, ()).item()))
+    mp.spawn(_nccl_trainer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = (torch.load(tmp_path / f"rank{r}.pt", weights_only=False) for r in (0, 1))
+    assert a["updates"] == b["updates"] > 0 and a["size"] == b["size"] == 2 * 32 * 12 and a["ptr"] == b["ptr"]
+    for k in a["store"]:
+        assert torch.equal(a["store"][k], b["store"][k]), k                      # identical replay contents
+    assert torch.equal(a["priority"], b["priority"]) and a["max_priority"] == b["max_priority"]
+    for mod in ("actor", "critic1"):
+        for k in a[mod]:
+            torch.testing.assert_close(a[mod][k], b[mod][k], rtol=0, atol=0, msg=f"{mod}.{k}")   # identical weights
+    assert torch.equal(a["log_alpha"], b["log_alpha"])
+    assert not torch.equal(a["masks0"], b["masks0"])                           # different scenarios per rank
+    # rank 0's half of every gathered step comes first: the first 32 stored actions are rank 0's own
+    assert a["res"]["world_size"] == 2 and a["res"]["nccl_time_share"] >= 0.0

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--method", default="cfw")
+    ap.add_argument("--out", default="", help="also write the JSON line to this file (rank 0)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -38,6 +39,9 @@ def main():
                          "batch_size": tr.cfg["batch_size"], "update_every": tr.cfg["update_every"],
                          "hidden_dim": tr.cfg["hidden_dim"], "gat_layers": tr.cfg["gat_layers"]}
         print(json.dumps(res), flush=True)
+        if args.out:
+            with open(args.out, "w") as fh:
+                json.dump(res, fh, indent=1)
     if world > 1:
         dist.destroy_process_group()
 
