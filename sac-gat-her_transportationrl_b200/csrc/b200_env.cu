@@ -4,6 +4,7 @@
 #include "b200_common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -167,6 +168,155 @@ __global__ void __launch_bounds__(kFeatWarps * 32) features_kernel(FeatParams p)
             ef[e * 6 + 0] = t0n; ef[e * 6 + 1] = capn; ef[e * 6 + 2] = vc; ef[e * 6 + 3] = d ? 1.0f : 0.0f;
             ef[e * 6 + 4] = goal_b[e] ? 1.0f : 0.0f; ef[e * 6 + 5] = (float)e / (float)max(E - 1, 1);
         }
+    }
+}
+
+// Small networks (N <= 32, e.g. Sioux Falls): ONE WARP per scenario, LANE = BFS SOURCE.  The active
+// out-neighbours of every node are a 32-bit mask, so a lane expands its own breadth-first search one
+// (node, successor) pair per trip - every lane has about as many pairs as there are undamaged links, so the
+// warp stays converged without any level synchronisation - keeping depth / path counts / BFS order /
+// dependencies in shared-memory columns of its own (row = node, column = lane: conflict-free whatever node
+// a lane touches).  The dependency pass walks the BFS order backwards with one division per node
+// ((1 + delta[w]) / sigma[w], reused by every predecessor of w).  About 6x fewer warp-instructions per
+// state than one warp per source (features_kernel), which remains the path of larger networks.
+constexpr int kFeatSmallWarps = 4;
+
+template <typename REAL>
+__global__ void __launch_bounds__(kFeatSmallWarps * 32) features_small_kernel(FeatParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = p.N, E = p.E, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kFeatSmallWarps + warp;
+    if (b >= p.B) return;
+    const unsigned FULL = 0xffffffffu;
+    // per warp: delta f64 [N][32] | coef f64 [N][32] | sigma f32 [N][32] | depth u8 [N][32] | order u8 [N][32] | adj u32 [32]
+    const size_t stride = (size_t)N * 32 * (8 + 8 + 4 + 1 + 1) + 128;
+    unsigned char *wb = smem + stride * warp;
+    double *delta = (double *)wb, *coef = delta + N * 32;
+    float *sigma = (float *)(coef + N * 32);
+    uint8_t *depth = (uint8_t *)(sigma + N * 32), *order = depth + N * 32;
+    unsigned *adj = (unsigned *)(order + N * 32);
+    const size_t off = (size_t)b * E;
+    const uint8_t *dmg_b = p.dmg + off, *goal_b = p.goal + off;
+    const REAL *flow_b = (const REAL *)p.flow + off;
+    // active out-neighbour masks; nodes of the edge-induced subgraph of undamaged links
+    unsigned mine = 0;
+    if (lane < N)
+        for (int k = __ldg(p.out_ptr + lane); k < __ldg(p.out_ptr + lane + 1); ++k)
+            if (!dmg_b[__ldg(p.out_eid + k)]) mine |= 1u << __ldg(p.out_dst + k);
+    adj[lane] = mine;
+    unsigned has_in = mine;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) has_in |= __shfl_xor_sync(FULL, has_in, sft);
+    const unsigned insub = has_in | __ballot_sync(FULL, mine != 0);
+    __syncwarp();
+    const int s = lane;
+    const bool src_ok = s < N && ((insub >> s) & 1u);
+    for (int v = 0; v < N; ++v) { depth[v * 32 + lane] = 0xff; delta[v * 32 + lane] = 0.0; }
+    int qt = 0;
+    if (src_ok) { depth[s * 32 + lane] = 0; sigma[s * 32 + lane] = 1.0f; order[lane] = (uint8_t)s; qt = 1; }
+    // ---- forward: BFS order, depths, shortest-path counts; one (node, successor) pair per trip
+    {
+        int qh = 0, v = 0, dv = 0;
+        unsigned rem = 0;
+        float sv = 0.0f;
+        bool live = src_ok;
+        while (__any_sync(FULL, live)) {
+            if (live && rem == 0) {
+                if (qh < qt) { v = order[qh * 32 + lane]; ++qh; rem = adj[v]; dv = depth[v * 32 + lane]; sv = sigma[v * 32 + lane]; }
+                else live = false;
+            }
+            if (live && rem) {
+                const int w = __ffs(rem) - 1;
+                rem &= rem - 1;
+                const int dw = depth[w * 32 + lane];
+                if (dw == 0xff) {
+                    depth[w * 32 + lane] = (uint8_t)(dv + 1);
+                    sigma[w * 32 + lane] = sv;
+                    order[qt * 32 + lane] = (uint8_t)w;
+                    ++qt;
+                } else if (dw == dv + 1) {
+                    sigma[w * 32 + lane] += sv;
+                }
+            }
+        }
+    }
+    // ---- backward: dependencies in reverse BFS order; coef[w] = (1 + delta[w]) / sigma[w] once per node
+    {
+        int qi = qt, v = 0, dv = 0;
+        unsigned rem = 0;
+        double acc = 0.0;
+        bool live = src_ok, open = false;
+        while (__any_sync(FULL, live)) {
+            if (live && rem == 0) {
+                if (open) {   // node v is complete
+                    const double sg = (double)sigma[v * 32 + lane];
+                    const double dl = sg * acc;
+                    delta[v * 32 + lane] = dl;
+                    coef[v * 32 + lane] = (1.0 + dl) / sg;
+                    open = false;
+                }
+                if (qi > 0) { --qi; v = order[qi * 32 + lane]; rem = adj[v]; dv = depth[v * 32 + lane]; acc = 0.0; open = true; }
+                else live = false;
+            }
+            if (live && rem) {
+                const int w = __ffs(rem) - 1;
+                rem &= rem - 1;
+                if (depth[w * 32 + lane] == dv + 1) acc += coef[w * 32 + lane];
+            }
+        }
+        if (src_ok) delta[s * 32 + lane] = 0.0;   // the source itself is not counted (reference: networkx)
+    }
+    __syncwarp();
+    // ---- betweenness of node `lane` = sum over sources (fixed order), then the scalars of the state
+    double bw = 0.0;
+    for (int v = 0; v < N; ++v) {
+        double x = delta[v * 32 + lane];   // lane = source column of row v
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) x += __shfl_xor_sync(FULL, x, sft);
+        if (lane == v) bw = x;
+    }
+    const double n_sub = (double)__popc(insub);
+    const double scale = n_sub > 2.0 ? 1.0 / ((n_sub - 1.0) * (n_sub - 2.0)) : 1.0;
+    double bmax = bw;
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) bmax = fmax(bmax, __shfl_xor_sync(FULL, bmax, sft));
+    double part[4] = {0, 0, 0, 0};   // goal total, remaining, active count, active flow sum
+    for (int e = lane; e < E; e += 32) {
+        part[0] += goal_b[e];
+        part[1] += (goal_b[e] && dmg_b[e]) ? 1.0 : 0.0;
+        if (!dmg_b[e]) { part[2] += 1.0; part[3] += (double)flow_b[e]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) part[i] += __shfl_xor_sync(FULL, part[i], sft);
+    const float bw_max = (float)(bmax * scale);
+    const float remaining_ratio = (float)(part[1] / fmax(part[0], 1.0));
+    const double avg_flow = part[2] > 0.0 ? part[3] / part[2] : 0.0;
+    const float avg_flow_norm = (float)(avg_flow / fmax(p.total_demand / (double)max(E, 1), 1.0));
+    const float log_tstt = (float)log10(fmax(p.tstt[b], 1.0));
+    if (lane < N) {
+        float x = (float)(bw * scale);
+        if (p.bw_raw) p.bw_raw[(size_t)b * N + lane] = x;
+        if (bw_max > 0.0f) x = x / bw_max;
+        *(float4 *)(p.node_feat + ((size_t)b * N + lane) * 4) = make_float4(x, remaining_ratio, avg_flow_norm, log_tstt);
+    }
+    float *ef = p.edge_feat + off * 6;
+    const double lt0 = log10(p.max_t0 + 1.0), lcap = log10(p.max_cap0 + 1.0);
+    for (int e = lane; e < E; e += 32) {
+        const bool d = dmg_b[e] != 0;
+        const float cap = d ? (float)p.capacity_damage : __ldg(p.cap0 + e);
+        const float t0n = (float)((double)log10f(__ldg(p.t0 + e) + 1.0f) / lt0);
+        const float capn = (float)((double)log10f(cap + 1.0f) / lcap);
+        float vc = 0.0f;
+        if (!d) {
+            vc = (float)flow_b[e] / fmaxf(cap, 1e-6f);
+            vc = log1pf(vc);
+            vc = fminf(fmaxf(vc, 0.0f), 10.0f);
+        }
+        ef[e * 6 + 0] = t0n; ef[e * 6 + 1] = capn; ef[e * 6 + 2] = vc; ef[e * 6 + 3] = d ? 1.0f : 0.0f;
+        ef[e * 6 + 4] = goal_b[e] ? 1.0f : 0.0f; ef[e * 6 + 5] = (float)e / (float)max(E - 1, 1);
     }
 }
 
@@ -347,6 +497,14 @@ extern "C" int b200_state_features(const b200_graph *g, int B, int prec, const v
     p.flow = flow; p.dmg = dmg; p.goal = goal; p.tstt = tstt; p.total_demand = g->total_demand;
     p.capacity_damage = capacity_damage; p.max_t0 = g->max_t0; p.max_cap0 = g->max_cap0;
     p.node_feat = node_feat; p.edge_feat = edge_feat; p.bw_raw = betweenness_raw;
+    if (g->N <= 32 && !getenv("B200_FEATURES_GENERIC")) {   // lane-per-source kernel (Sioux Falls class)
+        const size_t smem = ((size_t)g->N * 32 * (8 + 8 + 4 + 1 + 1) + 128) * kFeatSmallWarps;
+        auto kern = prec == B200_F32 ? features_small_kernel<float> : features_small_kernel<double>;
+        B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(B + kFeatSmallWarps - 1) / kFeatSmallWarps, kFeatSmallWarps * 32, smem, (cudaStream_t)stream>>>(p);
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    }
     int warps = kFeatWarps;
     auto smem_for = [&](int w) {
         return (size_t)((g->E + 15) & ~15) + (size_t)((g->N + 15) & ~15) + 64 * 8 +
