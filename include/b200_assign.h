@@ -12,8 +12,11 @@
  *    b200_last_error() returns a static string for the calling thread's last failure;
  *  - all array arguments of the compute calls are DEVICE pointers owned by the caller (torch
  *    tensors in our host code); the library allocates nothing per call (one exception: the general
- *    fused kernel keeps a trees workspace inside the handle, grown on first use); calls are asynchronous
- *    on the caller's stream (pass the cudaStream_t as a void*; NULL = legacy default stream);
+ *    fused kernel keeps per-CTA workspaces - previous trees, hierarchy weights - inside the handle, grown on
+ *    first use); calls are asynchronous on the caller's stream (pass the cudaStream_t as a void*; NULL =
+ *    legacy default stream).  A HANDLE SERVES ONE STREAM / THREAD AT A TIME: those workspaces and the
+ *    "last launch" fields are per handle, so concurrent b200_assign calls on one handle would share them.
+ *    Use one handle (one b200_graph_create) per concurrent stream;
  *  - batch layout: [B][E] / [B][O][N] row-major, one scenario per row ("scenario-major");
  *  - prec: B200_F32 keeps the reference's dtypes (fp32 flow/cost/TSTT sum, fp64 distances),
  *    B200_F64 keeps all link state in double.  `real` below means float or double by prec;

@@ -39,7 +39,6 @@ class GraphData:
     od_demand: Dict[Tuple[int, int], float]
 
 
-_OD_ENTRY = re.compile(r"\s*(-?\d+)\s*:\s*([^;:\s]+)\s*")
 
 
 def _significant_lines(path: str):

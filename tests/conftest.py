@@ -16,7 +16,8 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    # a gpu-marked test without a device is an error on the GPU box, a skip elsewhere
+    # a gpu-marked test without a device is a skip here; on a box that is SUPPOSED to have a GPU
+    # (B200_REQUIRE_GPU=1) it is an error, so a broken driver cannot pass as "all skipped"
     try:
         import torch
         has_gpu = torch.cuda.is_available()
@@ -24,6 +25,8 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = False
     if has_gpu:
         return
+    if os.environ.get("B200_REQUIRE_GPU") and any("gpu" in item.keywords for item in items):
+        raise pytest.UsageError("B200_REQUIRE_GPU is set but torch sees no CUDA device")
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:
         if "gpu" in item.keywords:
