@@ -16,7 +16,6 @@ and to hand synthetic networks to any TNTP consumer.
 """
 from __future__ import annotations
 
-import re
 from dataclasses import dataclass
 from typing import Dict, List, Tuple
 
