@@ -354,3 +354,32 @@ def test_reset_where_runs_on_the_device_and_fixed_damage_semantics(b200env, nati
     first = c.is_damaged.clone()
     c.reset()
     assert torch.equal(c.is_damaged, first)
+
+
+def test_feature_kernels_agree_on_small_networks(b200env, native_lib, sf_graph, monkeypatch):
+    """Networks up to 32 nodes take the lane-per-source feature kernel (one warp per scenario);
+    B200_FEATURES_GENERIC routes them through the warp-per-source kernel of the larger networks.  Both
+    must give the same betweenness / features (summation orders differ: 1e-6), also on a lattice with
+    dead-end-free one-way structure removed links, an undamaged and a heavily damaged network."""
+    from oracle.c_oracle import COracle
+    for g in (sf_graph, b200env.synthetic.small_grid(4, 5, 6, seed=3)):
+        orc = COracle.from_graph_data(g)
+        E = len(g.edges)
+        rng = np.random.default_rng(17)
+        B = 40
+        dmg = (rng.random((B, E)) < 0.3).astype(np.uint8)
+        dmg[0] = 0
+        dmg[1] = (rng.random(E) < 0.8).astype(np.uint8)          # most links gone: several unreachable pairs
+        flow = (rng.random((B, E)) * 5000).astype(np.float32)
+        tstt = rng.random(B) * 300 + 1
+        d = torch.device("cuda", 0)
+        args = lambda: (torch.from_numpy(flow).to(d), torch.from_numpy(dmg).to(d), torch.from_numpy(dmg).to(d),  # noqa: E731
+                        torch.from_numpy(tstt).to(d), 1e-3)
+        small = b200env.AssignmentEngine(b200env.Network(g), d, "fp32").state_features(*args(), return_raw_betweenness=True)
+        monkeypatch.setenv("B200_FEATURES_GENERIC", "1")
+        generic = b200env.AssignmentEngine(b200env.Network(g), d, "fp32").state_features(*args(), return_raw_betweenness=True)
+        monkeypatch.delenv("B200_FEATURES_GENERIC")
+        for a, b_ in zip(small, generic):
+            np.testing.assert_allclose(a.cpu().numpy(), b_.cpu().numpy(), rtol=2e-6, atol=1e-7)
+        for b in (0, 1, 7, 39):
+            np.testing.assert_allclose(small[2][b].cpu().numpy(), orc.betweenness(dmg[b]), rtol=2e-5, atol=1e-9)
