@@ -16,8 +16,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.environ.get("B200_LIB", os.path.join(PKG_DIR, "libb200assign.so"))  # env override: kernel A/B runs
 SOURCES = ["b200_graph.cu", "b200_cch.cu", "b200_assign.cu", "b200_assign_small.cu", "b200_assign_static.cu", "b200_env.cu",
            "b200_gat.cu"]
-HEADERS = ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", "b200_assign_static.cuh", "b200_topo_siouxfalls.h",
-           os.path.join("..", "..", "include", "b200_assign.h")]
+HEADERS = ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", "b200_assign_static.cuh", "b200_assign_static_grp.cuh",
+           "b200_topo_siouxfalls.h", os.path.join("..", "..", "include", "b200_assign.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -70,7 +70,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     deps = {"b200_assign.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
             "b200_assign_small.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_small.cuh", api],
             "b200_assign_static.cu": ["b200_common.cuh", "b200_assign_internal.cuh", "b200_assign_static.cuh",
-                                      "b200_topo_siouxfalls.h", api],
+                                      "b200_assign_static_grp.cuh", "b200_topo_siouxfalls.h", api],
             "b200_graph.cu": ["b200_common.cuh", api], "b200_env.cu": ["b200_common.cuh", api],
             "b200_cch.cu": ["b200_common.cuh", "b200_assign_internal.cuh", api],
             "b200_gat.cu": ["b200_common.cuh", api]}
@@ -172,7 +172,8 @@ def specialize(num_nodes: int, row, col, t0, origins, verbose: bool = False) -> 
                          f"E <= {SPECIALIZE_MAX_LINKS}, origins <= 32)")
     h = hashlib.sha1()
     h.update(np.int64(num_nodes).tobytes() + row.tobytes() + col.tobytes())
-    for dep in ("b200_static_plugin.cu", "b200_assign_static.cuh", "b200_assign_internal.cuh", "b200_common.cuh"):
+    for dep in ("b200_static_plugin.cu", "b200_assign_static.cuh", "b200_assign_static_grp.cuh", "b200_assign_internal.cuh",
+                "b200_common.cuh"):
         with open(os.path.join(CSRC, dep), "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -112,12 +112,12 @@ def _cch_levels(edges, tris):
     return level
 
 
-def _cch_batches(edges, tris, level, key):
-    """Customization batches: edges of one level, most triangles first, 32 per batch."""
+def _cch_batches(edges, tris, level, key, width=32):
+    """Customization batches: edges of one level, most triangles first, `width` per batch."""
     batches = []
     for L in range(1, max(level.values(), default=0) + 1):
         es = sorted((e for e in edges if level[e] == L), key=lambda e: (-len(tris[e]), key(e)))
-        batches += [es[c:c + 32] for c in range(0, len(es), 32)]
+        batches += [es[c:c + width] for c in range(0, len(es), width)]
     return batches
 
 
@@ -196,21 +196,28 @@ def emit_cch(N, koff, src) -> str:
     inf_slot, dummy_slot = cw, cw + 1
     orig = set(zip(tails, heads))
     corig = [slot_of[(tails[k], heads[k])] for k in range(len(tails))]
-    # customization batches: an edge is final once the two lower edges of each of its triangles are
-    tab, batch_t = [], []
-    for chunk in _cch_batches(edges, tris, _cch_levels(edges, tris), key=lambda e: slot_of[e]):
-        T = len(tris[chunk[0]])
-        batch_t.append(T)
-        tab += [(slot_of[e] * 8) | (0 if e in orig else 0x8000) for e in chunk]
-        tab += [(dummy_slot * 8) | 0x8000] * (32 - len(chunk))
-        for t in range(T):
-            for e in chunk:
-                if t < len(tris[e]):
-                    v = tris[e][t]
-                    tab.append((slot_of[(e[0], v)] * 8) | ((slot_of[(v, e[1])] * 8) << 16))
-                else:
-                    tab.append((inf_slot * 8) | ((inf_slot * 8) << 16))
-            tab += [(inf_slot * 8) | ((inf_slot * 8) << 16)] * (32 - len(chunk))
+    # customization batches: an edge is final once the two lower edges of each of its triangles are.
+    # Two tables: 32 edges per batch (one warp per scenario) and N edges per batch (grouped kernel: N
+    # lanes per scenario, several scenarios per group of warps); rows are padded to 32 words either way.
+    def table(width):
+        tab, batch_t = [], []
+        for chunk in _cch_batches(edges, tris, _cch_levels(edges, tris), key=lambda e: slot_of[e], width=width):
+            T = len(tris[chunk[0]])
+            batch_t.append(T)
+            tab += [(slot_of[e] * 8) | (0 if e in orig else 0x8000) for e in chunk]
+            tab += [(dummy_slot * 8) | 0x8000] * (32 - len(chunk))
+            for t in range(T):
+                for e in chunk:
+                    if t < len(tris[e]):
+                        v = tris[e][t]
+                        tab.append((slot_of[(e[0], v)] * 8) | ((slot_of[(v, e[1])] * 8) << 16))
+                    else:
+                        tab.append((inf_slot * 8) | ((inf_slot * 8) << 16))
+                tab += [(inf_slot * 8) | ((inf_slot * 8) << 16)] * (32 - len(chunk))
+        return tab, batch_t
+
+    tab, batch_t = table(32)
+    gtab, gbatch_t = table(min(N, 32))
 
     def arr(xs):
         return "{" + ", ".join(str(int(x)) for x in xs) + "}"
@@ -234,6 +241,10 @@ def emit_cch(N, koff, src) -> str:
     static constexpr int CORIG[{len(corig)}] = {arr(corig)};
     static constexpr int CZ_T[{max(len(batch_t), 1)}] = {arr(batch_t or [0])};
     static constexpr unsigned CZ_TAB[{max(len(tab), 1)}] = {arr(tab or [0])};
+    // the same customization in batches of N edges (grouped kernel: lane o of a scenario takes word o of a row)
+    static constexpr int CZG_NB = {len(gbatch_t)}, CZG_LEN = {len(gtab)};
+    static constexpr int CZG_T[{max(len(gbatch_t), 1)}] = {arr(gbatch_t or [0])};
+    static constexpr unsigned CZG_TAB[{max(len(gtab), 1)}] = {arr(gtab or [0])};
 """
 
 

@@ -97,7 +97,7 @@ struct b200_graph {
     int static_ok, st_intq, force_small;
     void *plugin_launch;   // launcher of the on-demand plugin that matched this topology (else built-in)
     int32_t *st_origpos;
-    unsigned char *st_blob32, *st_blob64, *st_blob_i32;
+    unsigned char *st_blob32, *st_blob64, *st_blob_i32, *st_blob_grp;
     // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): the down row stream
     // (batches of 1 + D rows of 32 words), one up row stream per origin (row pairs, up_off[O + 1]), the select stream,
     // customization tables (initial weight per filled edge, rows of 32 edges

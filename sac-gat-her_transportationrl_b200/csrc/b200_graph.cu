@@ -226,7 +226,7 @@ extern "C" int b200_graph_destroy(b200_graph *g)
     void *ptrs[] = {g->topo, g->row, g->col, g->t0, g->cap0, g->t0_csc, g->cap0_csc, g->origins, g->origin_slot,
                     g->od_ptr, g->od_dst, g->od_q64, g->od_q32, g->out_ptr, g->out_dst, g->out_eid,
                     g->small_blob32, g->small_blob64, g->small_blob_i32, g->small_eid, g->small_wpos,
-                    g->tree_ws, g->topo16, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32};
+                    g->tree_ws, g->topo16, g->st_origpos, g->st_blob32, g->st_blob64, g->st_blob_i32, g->st_blob_grp};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     b200_cch_destroy(g);

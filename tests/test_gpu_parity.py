@@ -645,20 +645,27 @@ def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, n
     hierarchy when every path sum is exact in fp64 (fp32 link state, host-checked); B200_NO_CCH forces
     the Gauss-Seidel sweeps.  Both must give the same bits as each other and as the C oracle, for every
     method, cold and warm start; fp64 link state and a cost range that breaks exactness must NOT take
-    the hierarchy."""
+    the hierarchy.  The fixed-step methods run the grouped variant (4 scenarios x 24 origin lanes on 3
+    warps, last_config cch == 2; B200_STATIC_NO_GRP=1 keeps one warp per scenario): same bits again."""
     G = golden("sf_batch4096_fw_k20.npz")
     masks = _masks_from_idx(G["dmg"][:512], 76)
     cch = _engine(b200env, sf_graph, "fp32")
+    monkeypatch.setenv("B200_STATIC_NO_GRP", "1")
+    one = _engine(b200env, sf_graph, "fp32")
+    monkeypatch.delenv("B200_STATIC_NO_GRP")
     monkeypatch.setenv("B200_NO_CCH", "1")
     gs = _engine(b200env, sf_graph, "fp32")
     monkeypatch.delenv("B200_NO_CCH")
     for method, K in (("fw", 20), ("msa", 20), ("cfw", 12), ("fw_ls", 8)):
         a = _assign(cch, masks, K, method)
-        assert cch.last_config["cch"] == 1 and cch.kernel_name == "assign_static_kernel"
+        assert cch.last_config["cch"] == (2 if method in ("fw", "msa") else 1) and cch.kernel_name == "assign_static_kernel"
         b = _assign(gs, masks, K, method)
         assert gs.last_config["cch"] == 0
+        c = _assign(one, masks, K, method)
+        assert one.last_config["cch"] == 1
         for key in ("flow", "tstt", "gap", "unassigned", "status"):
             assert np.array_equal(a[key], b[key]), (method, key)
+            assert np.array_equal(a[key], c[key]), (method, key, "grouped vs one warp per scenario")
         if method in ("fw", "msa"):
             for s in range(0, 512, 32):
                 o = sf_oracle.assign(masks[s], None, K, method)
@@ -672,6 +679,29 @@ def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, n
     # undamaged network, free-flow ties everywhere (iteration 0 of a cold start)
     z = np.zeros((2, 76), np.uint8)
     assert np.array_equal(_assign(cch, z, 20, "fw")["flow"], _assign(gs, z, 20, "fw")["flow"])
+    # grouped kernel: a batch that is not a multiple of the group, and rows switched off by `active`
+    # (those keep every output they had)
+    for n in (1, 3, 5, 7):
+        r = _assign(cch, masks[:n], 6, "fw")
+        assert cch.last_config["cch"] == 2
+        q = _assign(gs, masks[:n], 6, "fw")
+        for key in ("flow", "tstt", "gap", "unassigned", "status"):
+            assert np.array_equal(r[key], q[key]), (n, key)
+    d = _dev()
+    act = np.ones(37, np.uint8)
+    act[[0, 5, 6, 7, 36]] = 0
+    flow = torch.full((37, 76), 7.0, dtype=torch.float32, device=d)
+    out = {k: torch.full((37,), -3, dtype=torch.int32 if k == "status" else torch.float64, device=d)
+           for k in ("tstt", "gap", "unassigned", "status")}
+    got = cch.assign(torch.from_numpy(masks[:37]).to(d), flow, 6, "fw", out=out, active=torch.from_numpy(act).to(d))
+    assert cch.last_config["cch"] == 2
+    torch.cuda.synchronize()
+    on = act.astype(bool)
+    ref_warm = _assign(gs, masks[:37], 6, "fw", flow0=np.full((37, 76), 7.0, np.float32))
+    for key in ("flow", "tstt", "gap", "unassigned", "status"):
+        v = got[key].cpu().numpy()
+        assert np.array_equal(v[on], ref_warm[key][on]), key
+        assert np.all(v[~on] == (7.0 if key == "flow" else -3)), key
     # guards: double link state, and a BPR exponent whose clipped cost range is not exactly summable
     f64 = _engine(b200env, sf_graph, "fp64")
     _assign(f64, masks[:4], 5, "fw")
