@@ -394,11 +394,12 @@ def run_ours(args) -> None:
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic_bytes(), "peak_source": peak_src,
-                         "kernel": eng.kernel_name + "<float>", "kernel_ms": 1e3 * kern_s,
+                         "kernel": ("assign_static_grp_kernel<TopoSiouxFalls>" if eng.last_config.get("cch") == 2
+                                    else eng.kernel_name + "<float>"), "kernel_ms": 1e3 * kern_s,
                          "algorithmic_bytes_per_launch": bytes_per_assignment * B,
                          "note": "algorithmic bytes = K*(33E+8ON) per scenario (SURVEY.md 8d); the working set is "
                                  "register/shared-memory resident (traffic = ncu DRAM bytes per launch), the "
-                                 "binding limit is warp-instruction issue (DESIGN.md section 4)"},
+                                 "binding limit is the shared-memory wavefront pipe (DESIGN.md section 4)"},
             "quality": {"median_relative_gap_at_K": gap_med, "tstt_checksum": tstt_chk},
         }
         line["other_configs"] = other

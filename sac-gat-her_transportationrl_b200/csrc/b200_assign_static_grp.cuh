@@ -28,7 +28,7 @@ struct GrpShape {
                               : util(4) > util(2) && util(4) > util(1) ? 4
                               : util(2) > util(1) ? 2 : 1;
     static constexpr int GS = GW * 32 / OL, TH = GW * 32;
-    static constexpr bool worthwhile = util(GW) > util(1) + 100;   // > 10 points fewer idle lanes than one warp per scenario
+    static constexpr bool worthwhile = T::N <= 32 && util(GW) > util(1) + 100;   // > 10 points fewer idle lanes than one warp per scenario
 };
 
 template <class T>
@@ -45,7 +45,8 @@ struct GrpLayout {
                          TAB_WPOS = TAB_EID + EP, TAB_CPOS = TAB_WPOS + EP, TAB_CZ = calign16(TAB_CPOS + EP * 2);
     static constexpr int BLOB = TAB_CZ, BLOB_ALL = calign16(TAB_CZ + T::CZG_LEN * 4);
     // columns [N][TH]
-    static constexpr int WORD = 0, STK = WORD + N * TH * 4, PU = STK + N * TH, PK = PU + N * TH, COLS = calign16(PK + N * TH);
+    // packed subtree word u32 | tree parent + in-link slot (parent | slot << 8) u16 | Kahn stack u8
+    static constexpr int WORD = 0, PUK = WORD + N * TH * 4, STK = PUK + N * TH * 2, COLS = calign16(STK + N * TH);
     // per scenario
     static constexpr int WPAD = woff<T>(N);
     static constexpr int S_W = 0, S_CW = S_W + calign16(WPAD * 8), S_AUX = S_CW + calign16((T::CW + 2) * 8),
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
     using L = GrpLayout<T>;
     constexpr int N = T::N, E = T::E, TH = S::TH, GS = S::GS, OL = S::OL;
     constexpr int LPT = (GS * E + TH - 1) / TH;   // (scenario, link) pairs per thread in S4
-    static_assert(N <= 254 && E <= 254, "tree tables are bytes");
+    static_assert(N <= 32 && E <= 254, "one origin lane per node (orphan mask is 32 bits), link slots are bytes");
     extern __shared__ __align__(16) unsigned char smem[];
     const int t = threadIdx.x, lane = t & 31;
     uint64_t *bar = (uint64_t *)smem;
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
     unsigned char *scen0 = cols + L::COLS;
     int *red = (int *)(scen0 + L::SCEN * GS);      // [GS][2]: unassigned demand, NaN flag
     unsigned *word = (unsigned *)(cols + L::WORD) + t;
-    uint8_t *stk = cols + L::STK + t, *pu = cols + L::PU + t, *pk = cols + L::PK + t;
+    uint8_t *stk = cols + L::STK + t;
+    uint16_t *puk = (uint16_t *)(cols + L::PUK) + t;
     unsigned char *sb = scen0 + L::SCEN * s;
     const uint32_t wbase = smem_u32(sb + L::S_W), wcb = smem_u32(sb + L::S_CW);
     int *auxi = (int *)(sb + L::S_AUX);
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
         });
         // ---- predecessor selection + children counts (packed word: pending children << 24 | subtree sum) ----
         static_for<0, N>([&](auto I) { word[decltype(I)::value * TH] = (unsigned)Qc[decltype(I)::value * 32]; });
+        unsigned orphan = 0;   // bit i: node i has no tree parent (the origin, or unreachable)
         static_for<0, N>([&](auto I) {
             constexpr int i = decltype(I)::value, k0 = T::KOFF[i], deg = T::KOFF[i + 1] - k0;
             const double dv = d[i];
@@ -223,9 +226,9 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
                 const double du = d[sk];
                 if (du + c[j] == dv && du <= bdu && reach) { bu = sk; bk = k; bdu = du; }
             });
-            pu[i * TH] = (uint8_t)bu;
-            pk[i * TH] = (uint8_t)bk;
+            puk[i * TH] = (uint16_t)(bu | (bk << 8));
             const bool has = bu != 255;
+            orphan |= has ? 0u : 1u << i;
             word[(has ? bu : i) * TH] += has ? kChild : 0u;
         });
         // ---- S3: subtree sums in Kahn order; link loads by atomics on the scenario's int32 array ------
@@ -233,10 +236,10 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
         int top = 0;
 #pragma unroll 4
         for (int i = 0; i < N; ++i) {
-            const int pi = pu[i * TH];
+            const bool none = (orphan >> i) & 1u;
             const unsigned wi = word[i * TH];
-            const bool tree = (i != orig) & (pi != 255);
-            unq += (pi == 255) ? (wi & (kChild - 1u)) : 0u;
+            const bool tree = (i != orig) & !none;
+            unq += none ? (wi & (kChild - 1u)) : 0u;
             const bool leaf = tree & (wi < kChild);
             if (leaf) stk[top * TH] = (uint8_t)i;
             top += leaf ? 1 : 0;
@@ -244,9 +247,10 @@ __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96
         while (__any_sync(FULL, top > 0)) {
             if (top > 0) {
                 const int v = stk[(--top) * TH];
-                const int u = pu[v * TH];
+                const unsigned uk = puk[v * TH];
+                const int u = uk & 255u;
                 const unsigned sv = word[v * TH];
-                if (sv != 0u && lane_live) atomicAdd(auxi + pk[v * TH], (int)sv);
+                if (sv != 0u && lane_live) atomicAdd(auxi + (uk >> 8), (int)sv);
                 const unsigned wu = word[u * TH] + sv - kChild;
                 word[u * TH] = wu;
                 if (wu < kChild && u != orig) stk[(top++) * TH] = (uint8_t)u;

@@ -9,6 +9,7 @@ out=gpurun_out
 lib=sac-gat-her_transportationrl_b200/libb200assign.so
 cap() {  # cap <name> <kernel regex> <skip> <keep report: 0|1> <command...>
   local name=$1 regex=$2 skip=$3 keep=$4; shift 4
+  if [ -n "${ONLY:-}" ] && [[ ! " $ONLY " =~ " $name " ]]; then return; fi   # ONLY="assign_static gat_fwd" bash tools/profile_r02.sh
   "$@" > $out/r02_${name}_plain.log 2>&1 || { echo "plain run of $name failed"; return; }
   ncu --set full --import-source on --clock-control none -k regex:$regex -s $skip -c 1 -f -o $out/r02_$name "$@" > $out/r02_${name}_ncu.log 2>&1
   { echo "# $name: $*"; grep -h "^{" $out/r02_${name}_plain.log | tail -3; python tools/ncu_rawsum.py $out/r02_$name.ncu-rep;
@@ -27,6 +28,7 @@ cap aon aon_kernel 2 0 python tools/measure_stages.py 65536 16384
 cap update update_kernel 2 0 python tools/measure_stages.py 65536 16384
 cap gat_fwd gat_fwd 2 0 python tools/measure_gat.py 4096 4 256
 cap gat_bwd gat_bwd 2 0 python tools/measure_gat.py 4096 4 256
+[ -n "${ONLY:-}" ] && { du -sh $out; exit 0; }
 python tools/measure_stages.py > $out/r02_stages.log 2>&1
 python tools/measure_features.py sf an cs > $out/r02_features.log 2>&1
 for h in 4 1; do python tools/measure_gat.py 8192 $h 256; done > $out/r02_gat.log 2>&1
