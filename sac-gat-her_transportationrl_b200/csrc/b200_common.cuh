@@ -45,7 +45,7 @@ void b200_set_error(const char *fmt, ...);
 // In-links of a node are stored in ascending tail-node order.
 struct b200_graph {
     int device;
-    int N, E, O, num_od, max_in_deg, num_sms;
+    int N, E, O, num_od, max_in_deg, max_out_deg, num_sms;
     double total_demand;
     // topology blob + offsets (in int32 elements)
     int32_t *topo;

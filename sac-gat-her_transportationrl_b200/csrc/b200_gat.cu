@@ -303,15 +303,20 @@ __global__ void __launch_bounds__(kGatThreads) gat_bwd_kernel(GatParams p)
 constexpr int kGrpThreads = 1024;
 
 struct GrpGeom {
-    int G;
+    int G, per_sm, threads;
     size_t slab_bytes, att_bytes, topo_bytes, scratch_bytes, total_fwd, total_bwd, graw_bytes;
 };
 
-inline GrpGeom grp_geom(int N, int E, int H, int C)
+// per_sm = 2: half-size groups, 16 warps, two CTAs per SM.  The two CTAs are in different phases most of the
+// time, so one's exposed waits (the first group's copy, the phase-1 / phase-2 hand-over) are covered by the
+// other's traffic; taken when a graph's slab is at most 50 KB (one head of 256 channels, four of 128 channels)
+inline GrpGeom grp_geom(int N, int E, int H, int C, int per_sm)
 {
     GrpGeom g;
     const size_t one = (size_t)N * H * C * 4;
-    g.G = (int)std::min<size_t>(8, std::max<size_t>(1, (100 * 1024) / one));
+    g.per_sm = per_sm;
+    g.threads = per_sm == 2 ? 512 : kGrpThreads;
+    g.G = (int)std::min<size_t>(8, std::max<size_t>(1, ((per_sm == 2 ? 50 : 100) * 1024) / one));
     g.slab_bytes = one * g.G;
     g.att_bytes = 2 * gat_pad16((size_t)g.G * N * H * 4) + 2 * gat_pad16((size_t)g.G * (E + N) * H * 4);   // + alpha (backward)
     g.topo_bytes = gat_pad16((size_t)(2 * (N + 1) + 4 * E) * 4);
@@ -562,6 +567,18 @@ __global__ void __launch_bounds__(kGrpThreads) gat_bwd_grp_kernel(GatParams p, i
     }
 }
 
+// geometry of the grouped kernels for this network: two CTAs per SM when they fit (B200_GAT_CTAS=1|2 forces)
+inline GrpGeom grp_pick(const b200_graph *g, int H, int C, bool bwd)
+{
+    const char *force = getenv("B200_GAT_CTAS");
+    const GrpGeom two = grp_geom(g->N, g->E, H, C, 2), one = grp_geom(g->N, g->E, H, C, 1);
+    const size_t need = bwd ? two.total_bwd : two.total_fwd;
+    const bool fits2 = C == 256 && (size_t)g->N * H * C * 4 <= 50 * 1024 && 2 * (need + 1024) <= 227 * 1024;   // 128 channels: measured 1-3 % slower
+    if (force && force[0] == '1') return one;
+    if (force && force[0] == '2' && (size_t)g->N * H * C * 4 <= 50 * 1024 && 2 * (need + 1024) <= 227 * 1024) return two;
+    return fits2 ? two : one;
+}
+
 // one warp per (node, head) pair of a graph, at most 32 warps: a CTA never carries idle warps, and
 // small slabs (one head) leave room for a second CTA on the SM
 int gat_threads(int N, int H) { return 32 * std::min(32, std::max(1, N * H)); }
@@ -601,12 +618,13 @@ extern "C" int b200_gat_edge_softmax_aggregate_fwd(const b200_graph *g, int B, i
     const bool narrow = g->max_in_deg + 1 <= 8;
     const bool att16 = ((size_t)g->N * H * 4) % 16 == 0 && ((size_t)(g->E + g->N) * H * 4) % 16 == 0;
     if (narrow && att16 && (C == 128 || C == 256) && !getenv("B200_GAT_SLAB")) {   // grouped staged path
-        const GrpGeom gg = grp_geom(g->N, g->E, H, C);
+        const GrpGeom gg = grp_pick(g, H, C, false);
         if (gg.total_fwd <= 226 * 1024) {
             auto kern = C == 256 ? gat_fwd_grp_kernel<2> : gat_fwd_grp_kernel<1>;
             B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg.total_fwd));
+            B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
             const int groups = (B + gg.G - 1) / gg.G;
-            kern<<<std::min(groups, g->num_sms), kGrpThreads, gg.total_fwd, st>>>(p, gg.G, gg.att_bytes, gg.topo_bytes);
+            kern<<<std::min(groups, g->num_sms * gg.per_sm), gg.threads, gg.total_fwd, st>>>(p, gg.G, gg.att_bytes, gg.topo_bytes);
             B200_CUDA(cudaGetLastError());
             return 0;
         }
@@ -649,15 +667,14 @@ extern "C" int b200_gat_edge_softmax_aggregate_bwd(const b200_graph *g, int B, i
         bool narrow_out = true;   // out-degree + self loop <= 8 as well (phase 2 uses the 8-entry scratch)
         const bool att16 = ((size_t)g->N * H * 4) % 16 == 0 && ((size_t)(g->E + g->N) * H * 4) % 16 == 0;
         if (narrow && att16 && (C == 128 || C == 256) && !getenv("B200_GAT_SLAB")) {
-            std::vector<int32_t> optr(g->N + 1);
-            B200_CUDA(cudaMemcpy(optr.data(), g->out_ptr, sizeof(int32_t) * (g->N + 1), cudaMemcpyDeviceToHost));
-            for (int v = 0; v < g->N; ++v) narrow_out = narrow_out && optr[v + 1] - optr[v] + 1 <= 8;
-            const GrpGeom gg = grp_geom(g->N, g->E, H, C);
+            narrow_out = g->max_out_deg + 1 <= 8;   // host copy of the degree: no device read-back on the training path
+            const GrpGeom gg = grp_pick(g, H, C, true);
             if (narrow_out && gg.total_bwd <= 226 * 1024) {
                 auto kern = C == 256 ? gat_bwd_grp_kernel<2> : gat_bwd_grp_kernel<1>;
                 B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg.total_bwd));
+                B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                 const int groups = (B + gg.G - 1) / gg.G;
-                kern<<<std::min(groups, g->num_sms), kGrpThreads, gg.total_bwd, st>>>(p, gg.G, gg.topo_bytes, gg.graw_bytes);
+                kern<<<std::min(groups, g->num_sms * gg.per_sm), gg.threads, gg.total_bwd, st>>>(p, gg.G, gg.topo_bytes, gg.graw_bytes);
                 B200_CUDA(cudaGetLastError());
                 return 0;
             }

@@ -160,6 +160,7 @@ extern "C" int b200_graph_create(int device, int N, int E, const int32_t *row, c
         // packed Kahn words of the general kernel: 4 bits of pending children, 28 bits of subtree demand
         int max_out = 0;
         for (int v = 0; v < N; ++v) max_out = std::max(max_out, out_ptr[v + 1] - out_ptr[v]);
+        g->max_out_deg = max_out;
         double max_origin = 0.0;
         for (int s2 = 0; s2 < O; ++s2) {
             double t = 0.0;
