@@ -98,6 +98,7 @@ struct b200_graph {
     void *plugin_launch;   // launcher of the on-demand plugin that matched this topology (else built-in)
     int32_t *st_origpos;
     unsigned char *st_blob32, *st_blob64, *st_blob_i32, *st_blob_grp;
+    int grp_force;   // B200_STATIC_NO_GRP=0: grouped static kernel whatever the batch size (tests)
     // customizable contraction hierarchy of the general fused kernel (b200_cch.cu): the down row stream
     // (batches of 1 + D rows of 32 words), one up row stream per origin (row pairs, up_off[O + 1]), the select stream,
     // customization tables (initial weight per filled edge, rows of 32 edges

@@ -501,8 +501,18 @@ def test_on_demand_specialised_kernel_for_another_small_network(b200env, native_
     special = b200env.AssignmentEngine(b200env.Network(g, specialize=True), _dev(), "fp32")
     special64 = b200env.AssignmentEngine(b200env.Network(g, specialize=True), _dev(), "fp64")
     assert special.kernel_name == "assign_static_kernel"
+    # the grouped variant of the plugin (20 origin lanes: 3 scenarios on 2 warps, 4 idle threads), forced at this
+    # small batch size
+    monkeypatch.setenv("B200_STATIC_NO_GRP", "0")
+    grouped = b200env.AssignmentEngine(b200env.Network(g, specialize=True), _dev(), "fp32")
+    monkeypatch.delenv("B200_STATIC_NO_GRP")
     for method in ("msa", "fw"):
         a, b = _assign(generic, masks, 20, method), _assign(special, masks, 20, method)
+        c = _assign(grouped, masks, 20, method)
+        if special.last_config["cch"]:      # strongly connected lattice: hierarchy sweeps, grouped kernel available
+            assert special.last_config["cch"] == 1 and grouped.last_config["cch"] == 2
+        for key in ("flow", "tstt", "gap", "unassigned", "status"):
+            assert np.array_equal(b[key], c[key]), (method, key, "grouped plugin kernel")
         assert np.array_equal(a["flow"], b["flow"]) and np.array_equal(a["tstt"], b["tstt"])
         assert np.array_equal(a["unassigned"], b["unassigned"]) and np.array_equal(a["status"], b["status"])
         for s_ in (0, 17, 39):
@@ -626,7 +636,14 @@ def test_sf_4096_flip_report(b200env, native_lib, sf_graph, golden, capsys):
     masks = _masks_from_idx(G["dmg"], 76)
     report = {}
     for precision, rtol in (("fp32", RTOL_F32), ("fp64", RTOL_F64)):
-        out = _assign(_engine(b200env, sf_graph, precision), masks, 20, "fw")
+        eng = _engine(b200env, sf_graph, precision)
+        out = _assign(eng, masks, 20, "fw")
+        # 4096 scenarios: fp32 takes the grouped hierarchy kernel, fp64 the Gauss-Seidel one; a small batch stays
+        # on one warp per scenario
+        assert eng.last_config["cch"] == (2 if precision == "fp32" else 0)
+        if precision == "fp32":
+            few = _assign(eng, masks[:64], 20, "fw")
+            assert eng.last_config["cch"] == 1 and np.array_equal(few["flow"], out["flow"][:64])
         err = np.abs(out["tstt"] - G["tstt_reset"]) / G["tstt_reset"]
         worst = int(np.argmax(err))
         report[precision] = dict(flips=int((err > rtol).sum()), worst_scenario=worst, worst_rel_err=float(err[worst]),
@@ -649,6 +666,7 @@ def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, n
     warps, last_config cch == 2; B200_STATIC_NO_GRP=1 keeps one warp per scenario): same bits again."""
     G = golden("sf_batch4096_fw_k20.npz")
     masks = _masks_from_idx(G["dmg"][:512], 76)
+    monkeypatch.setenv("B200_STATIC_NO_GRP", "0")    # grouped at any batch size (default: from 12 scenarios per SM)
     cch = _engine(b200env, sf_graph, "fp32")
     monkeypatch.setenv("B200_STATIC_NO_GRP", "1")
     one = _engine(b200env, sf_graph, "fp32")

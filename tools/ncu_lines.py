@@ -22,9 +22,23 @@ def sass_rows(rep):
     return [dict(zip(hdr, r)) for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
 
 
-def line_map(binary, kernel_sub):
-    """list of (file, line) per instruction index of the first function whose name contains kernel_sub"""
+def mangled_name(rep):
+    """mangled name of the (first) kernel in the report, or None"""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-kernel-base", "mangled"],
+                         capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(out.splitlines()) if r]
+    try:
+        i = rows[0].index("Kernel Name")
+        return rows[2][i]
+    except (ValueError, IndexError):
+        return None
+
+
+def line_map(binary, kernel_sub, want_len=None):
+    """list of (file, line) per instruction index of the function whose name contains kernel_sub; with several
+    template instantiations matching, the one whose instruction count equals the profiled one (want_len)"""
     tmp = tempfile.mkdtemp()
+    first = None
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(binary)], cwd=tmp, capture_output=True)
     for cubin in sorted(os.listdir(tmp)):
         txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
@@ -41,9 +55,16 @@ def line_map(binary, kernel_sub):
                 continue
             if fn and re.match(r"\s+/\*[0-9a-f]{4,}\*/", ln):
                 res[fn].append(cur)
-        for name, lst in res.items():
-            if kernel_sub in name and lst:
-                return name, lst
+        cands = [(name, lst) for name, lst in res.items() if kernel_sub in name and lst]
+        exact = [c for c in cands if want_len is not None and len(c[1]) == want_len]
+        if exact or cands:
+            found = (exact or cands)[0]
+            if first is None or exact:
+                first = found
+            if exact:
+                return first
+    if first:
+        return first
     raise SystemExit("kernel not found in " + binary)
 
 
@@ -51,7 +72,8 @@ def main():
     rep, binary, ksub = sys.argv[1:4]
     min_pct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.4
     rows = sass_rows(rep)
-    name, lines = line_map(binary, ksub)
+    exact = mangled_name(rep)   # the instantiation that was profiled, not the first one that matches the substring
+    name, lines = line_map(binary, exact if exact and ksub in exact else ksub, len(rows))
     if len(lines) != len(rows):
         print(f"# warning: {len(rows)} profiled instructions vs {len(lines)} in the binary (different build?)")
     agg = collections.defaultdict(lambda: [0, 0, 0])
