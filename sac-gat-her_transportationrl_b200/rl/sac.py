@@ -36,6 +36,21 @@ class SACOutput:
     probs: torch.Tensor  # [B, E]
 
 
+class _NarrowLayerNorm(nn.LayerNorm):
+    """``nn.LayerNorm`` over a handful of features (the 4 node / 6 link inputs).  torch's CUDA kernel for a feature
+    count that is not a multiple of 4 launches one thread block per row - 0.38 ms for the 77 824 link rows of 1024
+    scenarios, as long as a 1024 x 1024 projection - so the same formula (biased variance, eps inside the root) is
+    written with elementwise ops here.  Same parameters and state-dict keys."""
+
+    def forward(self, x):
+        if not x.is_cuda or self.normalized_shape[0] > 8:
+            return super().forward(x)
+        mean = x.mean(dim=-1, keepdim=True)
+        xc = x - mean
+        var = (xc * xc).mean(dim=-1, keepdim=True)
+        return xc * torch.rsqrt(var + self.eps) * self.weight + self.bias
+
+
 class _EdgeHead(nn.Module):
     """Shared body of Actor and Critic: norms -> encoder -> per-link MLP on
     [emb(src) | emb(dst) | edge_attr | global mean||max context]."""
@@ -43,8 +58,8 @@ class _EdgeHead(nn.Module):
     def __init__(self, network: Network, node_in: int, edge_in: int, hidden: int, embed: int, num_layers: int = 3,
                  encoder: Optional[GATEncoderB200] = None):
         super().__init__()
-        self.node_norm = nn.LayerNorm(node_in)
-        self.edge_norm = nn.LayerNorm(edge_in)
+        self.node_norm = _NarrowLayerNorm(node_in)
+        self.edge_norm = _NarrowLayerNorm(edge_in)
         self.encoder = encoder if encoder is not None else GATEncoderB200(network, node_in, hidden, embed,
                                                                           edge_dim=edge_in, num_layers=num_layers)
         self.edge_mlp = nn.Sequential(nn.Linear(embed * 4 + edge_in, hidden), nn.ReLU(), nn.Linear(hidden, 1))
@@ -82,13 +97,19 @@ class Critic(_EdgeHead):
 
 
 class DiscreteSAC:
+    _GRAPH_WARMUP = 3   # eager updates before the stages are captured
+
     def __init__(self, network: Network, node_in: int, edge_in: int, hidden: int, embed: int, num_layers: int = 3,
                  lr: float = 3e-4, actor_lr: Optional[float] = None, critic_lr: Optional[float] = None,
                  alpha_lr: Optional[float] = None, grad_clip: Optional[float] = None, gamma: float = 0.99,
                  target_tau: float = 0.005, target_entropy: Optional[float] = None, target_entropy_ratio: float = 0.1,
-                 alpha_init: float = 0.1, share_critic_encoder: bool = True, device="cuda"):
+                 alpha_init: float = 0.1, share_critic_encoder: bool = True, device="cuda", cuda_graph: bool = False):
         dev = torch.device(device)
         self.device = dev
+        # learner update as replayed CUDA graphs (see _update_graphed); Adam keeps its step count on the device
+        self.cuda_graph = bool(cuda_graph) and dev.type == "cuda"
+        self._graph, self._graph_calls = None, 0
+        cap = dict(capturable=True) if self.cuda_graph else {}
         mk = dict(network=network, node_in=node_in, edge_in=edge_in, hidden=hidden, embed=embed, num_layers=num_layers)
         self.actor = Actor(**mk).to(dev)
         self.share_critic_encoder = share_critic_encoder
@@ -111,16 +132,17 @@ class DiscreteSAC:
         actor_lr = lr if actor_lr is None else actor_lr
         critic_lr = lr if critic_lr is None else critic_lr
         alpha_lr = lr if alpha_lr is None else alpha_lr
-        self.actor_opt = torch.optim.Adam(self.actor.parameters(), lr=actor_lr)
+        self._actor_params = list(self.actor.parameters())
+        self.actor_opt = torch.optim.Adam(self._actor_params, lr=actor_lr, **cap)
         if share_critic_encoder:
             # exactly the reference's list (:119-123): the critics' input LayerNorms are not optimised
             self.critic_params = (list(self.critic_encoder.parameters()) + list(self.critic1.edge_mlp.parameters())
                                   + list(self.critic2.edge_mlp.parameters()))
         else:
             self.critic_params = list(self.critic1.parameters()) + list(self.critic2.parameters())
-        self.critic_opt = torch.optim.Adam(self.critic_params, lr=critic_lr)
+        self.critic_opt = torch.optim.Adam(self.critic_params, lr=critic_lr, **cap)
         self.log_alpha = torch.tensor(float(np.log(max(alpha_init, 1e-8))), requires_grad=True, device=dev)
-        self.alpha_opt = torch.optim.Adam([self.log_alpha], lr=alpha_lr)
+        self.alpha_opt = torch.optim.Adam([self.log_alpha], lr=alpha_lr, **cap)
         self.gamma, self.target_tau = gamma, target_tau
         self.target_entropy, self.target_entropy_ratio, self.grad_clip = target_entropy, target_entropy_ratio, grad_clip
 
@@ -137,58 +159,59 @@ class DiscreteSAC:
         log_prob = torch.log(probs.gather(1, action.unsqueeze(1)).squeeze(1) + 1e-8)
         return SACOutput(action=action, log_prob=log_prob, probs=probs)
 
-    def update(self, batch: Dict[str, torch.Tensor], weights: Optional[torch.Tensor] = None,
-               alpha_max: Optional[float] = None) -> Dict[str, torch.Tensor]:
-        """One learner step on a dense batch (keys of ``DeviceReplay.store``); losses as in :159-263."""
-        f32 = lambda k: batch[k].to(self.device, torch.float32)  # noqa: E731
-        node_x, edge_attr, mask = f32("node_x"), f32("edge_attr"), f32("action_mask")
-        nnode_x, nedge_attr, nmask = f32("next_node_x"), f32("next_edge_attr"), f32("next_action_mask")
-        action = batch["action"].to(self.device, torch.int64).unsqueeze(1)
-        reward, done = f32("reward"), f32("done")
-        w = torch.ones_like(reward) if weights is None else weights.to(self.device, torch.float32).expand_as(reward)
+    # ---- one learner step, in four stages separated by the (optional) gradient all-reduces -----------
+    # Each stage is a plain function of the tensors in ``s``; ``update`` runs them eagerly, or - with
+    # ``cuda_graph=True`` and a fixed batch shape - replays one captured CUDA graph per stage (about a thousand
+    # small launches per update otherwise: the update is launch-bound, 13 ms of GPU work in 18 ms of wall clock).
+    def _stage_critic(self, s) -> None:
         with torch.no_grad():
-            _, next_probs, _ = self.actor(nnode_x, nedge_attr, nmask)
-            q_next = torch.min(self.target1(nnode_x, nedge_attr), self.target2(nnode_x, nedge_attr))
+            _, next_probs, _ = self.actor(s["next_node_x"], s["next_edge_attr"], s["next_action_mask"])
+            q_next = torch.min(self.target1(s["next_node_x"], s["next_edge_attr"]),
+                               self.target2(s["next_node_x"], s["next_edge_attr"]))
             v_next = (next_probs * (q_next - self.alpha * torch.log(next_probs + 1e-8))).sum(dim=1)
-            target = reward + (1.0 - done) * self.gamma * v_next
-        q1_all, q2_all = self.critic1(node_x, edge_attr), self.critic2(node_x, edge_attr)
-        q1, q2 = q1_all.gather(1, action).squeeze(1), q2_all.gather(1, action).squeeze(1)
-        td_error = (target - q1).detach().abs()
-        critic_loss = (w * (F.mse_loss(q1, target, reduction="none") + F.mse_loss(q2, target, reduction="none"))).mean()
-        self.critic_opt.zero_grad(set_to_none=True)
+            target = s["reward"] + (1.0 - s["done"]) * self.gamma * v_next
+        q1_all, q2_all = self.critic1(s["node_x"], s["edge_attr"]), self.critic2(s["node_x"], s["edge_attr"])
+        q1, q2 = q1_all.gather(1, s["action"]).squeeze(1), q2_all.gather(1, s["action"]).squeeze(1)
+        s["td_errors"] = (target - q1).detach().abs()
+        critic_loss = (s["w"] * (F.mse_loss(q1, target, reduction="none") + F.mse_loss(q2, target, reduction="none"))).mean()
+        self.critic_opt.zero_grad(set_to_none=not s["static"])
         critic_loss.backward()
-        allreduce_mean_gradients(self.critic_params)
+        s["critic_loss"] = critic_loss.detach()
+        s["q_all"] = torch.min(q1_all, q2_all).detach()
+        s["q_taken"] = torch.min(q1, q2).detach().mean()
+
+    def _stage_actor(self, s) -> None:
         if self.grad_clip:
             torch.nn.utils.clip_grad_norm_(self.critic_params, max_norm=self.grad_clip)
         self.critic_opt.step()
-
-        _, probs, _ = self.actor(node_x, edge_attr, mask)
-        q_all = torch.min(q1_all, q2_all).detach()
+        _, probs, _ = self.actor(s["node_x"], s["edge_attr"], s["action_mask"])
         log_p = torch.log(probs + 1e-8)
-        actor_loss = (probs * (self.alpha.detach() * log_p - q_all)).sum(dim=1).mean()
-        self.actor_opt.zero_grad(set_to_none=True)
+        actor_loss = (probs * (self.alpha.detach() * log_p - s["q_all"])).sum(dim=1).mean()
+        self.actor_opt.zero_grad(set_to_none=not s["static"])
         actor_loss.backward()
-        actor_params = list(self.actor.parameters())
-        allreduce_mean_gradients(actor_params)
-        if self.grad_clip:
-            torch.nn.utils.clip_grad_norm_(actor_params, max_norm=self.grad_clip)
-        self.actor_opt.step()
+        s["actor_loss"] = actor_loss.detach()
+        s["probs"], s["log_p"] = probs.detach(), log_p.detach()
 
+    def _stage_alpha(self, s) -> None:
+        if self.grad_clip:
+            torch.nn.utils.clip_grad_norm_(self._actor_params, max_norm=self.grad_clip)
+        self.actor_opt.step()
         if self.target_entropy is None:
-            target_entropy = (self.target_entropy_ratio * torch.log((mask > 0).float().sum(dim=1) + 1e-8)).mean()
+            target_entropy = (self.target_entropy_ratio * torch.log((s["action_mask"] > 0).float().sum(dim=1) + 1e-8)).mean()
         else:
             target_entropy = self.target_entropy
-        probs_d, log_pd = probs.detach(), log_p.detach()
-        alpha_loss = -(self.log_alpha * (probs_d * (log_pd + target_entropy)).sum(dim=1)).mean()
-        self.alpha_opt.zero_grad(set_to_none=True)
+        alpha_loss = -(self.log_alpha * (s["probs"] * (s["log_p"] + target_entropy)).sum(dim=1)).mean()
+        self.alpha_opt.zero_grad(set_to_none=not s["static"])
         alpha_loss.backward()
-        allreduce_mean_gradients([self.log_alpha])
+        s["alpha_loss"] = alpha_loss.detach()
+
+    def _stage_finish(self, s) -> None:
         if self.grad_clip:
             torch.nn.utils.clip_grad_norm_([self.log_alpha], max_norm=self.grad_clip)
         self.alpha_opt.step()
         with torch.no_grad():
-            if alpha_max is not None:
-                self.log_alpha.clamp_(max=float(np.log(alpha_max)))
+            if s["alpha_max"] is not None:
+                self.log_alpha.clamp_(max=float(np.log(s["alpha_max"])))
             self.log_alpha.clamp_(min=float(np.log(0.01)))
             if self.share_critic_encoder:
                 self._soft_update(self.critic_encoder, self.target_encoder)
@@ -197,9 +220,85 @@ class DiscreteSAC:
             else:
                 self._soft_update(self.critic1, self.target1)
                 self._soft_update(self.critic2, self.target2)
-        return {"critic_loss": critic_loss.detach(), "actor_loss": actor_loss.detach(), "alpha": self.alpha.detach(),
-                "alpha_loss": alpha_loss.detach(), "policy_entropy": -(probs_d * log_pd).sum(dim=1).mean(),
-                "q_taken": torch.min(q1, q2).detach().mean(), "q_mean": q_all.mean(), "td_errors": td_error}
+            s["alpha"] = self.alpha.detach()
+            s["policy_entropy"] = -(s["probs"] * s["log_p"]).sum(dim=1).mean()
+            s["q_mean"] = s["q_all"].mean()
+
+    _STAGES = ("_stage_critic", "_stage_actor", "_stage_alpha", "_stage_finish")
+    _OUT_KEYS = ("critic_loss", "actor_loss", "alpha", "alpha_loss", "policy_entropy", "q_taken", "q_mean", "td_errors")
+    _IN_KEYS = ("node_x", "edge_attr", "action_mask", "next_node_x", "next_edge_attr", "next_action_mask", "reward", "done")
+
+    def _reduce_after(self, stage: int) -> None:
+        """Gradient averaging over ranks that follows stage ``stage`` (eager NCCL, between the stage graphs)."""
+        if stage == 0:
+            allreduce_mean_gradients(self.critic_params)
+        elif stage == 1:
+            allreduce_mean_gradients(self._actor_params)
+        elif stage == 2:
+            allreduce_mean_gradients([self.log_alpha])
+
+    def update(self, batch: Dict[str, torch.Tensor], weights: Optional[torch.Tensor] = None,
+               alpha_max: Optional[float] = None) -> Dict[str, torch.Tensor]:
+        """One learner step on a dense batch (keys of ``DeviceReplay.store``); losses as in :159-263."""
+        f32 = lambda k: batch[k].to(self.device, torch.float32)  # noqa: E731
+        s = {k: f32(k) for k in self._IN_KEYS}
+        s["action"] = batch["action"].to(self.device, torch.int64).unsqueeze(1)
+        s["w"] = (torch.ones_like(s["reward"]) if weights is None
+                  else weights.to(self.device, torch.float32).expand_as(s["reward"]))
+        s["alpha_max"], s["static"] = alpha_max, False
+        if self.cuda_graph and self.device.type == "cuda":
+            out = self._update_graphed(s)
+            if out is not None:
+                return out
+        # an eager update after the capture (a batch of another shape) must not move the gradient tensors the
+        # graphs write to: zero them in place instead of dropping them
+        s["static"] = self._graph is not None
+        for i, name in enumerate(self._STAGES):
+            getattr(self, name)(s)
+            self._reduce_after(i)
+        return {k: s[k] for k in self._OUT_KEYS}
+
+    def _update_graphed(self, s) -> Optional[Dict[str, torch.Tensor]]:
+        """Replay of the captured stage graphs.  The first ``_GRAPH_WARMUP`` updates run eagerly (they are real
+        updates and create the optimiser state and the gradient tensors); then the four stages are captured once
+        for this batch shape - gradients are zeroed in place from then on, so every tensor a graph touches keeps its
+        address - and every later update copies the batch into the static inputs and replays.  A batch of another
+        shape (or another ``alpha_max``) runs eagerly."""
+        g = self._graph
+        key = (tuple(s["node_x"].shape), tuple(s["edge_attr"].shape), s["alpha_max"])
+        if g is None:
+            self._graph_calls += 1
+            if self._graph_calls <= self._GRAPH_WARMUP:
+                return None
+            static = {k: s[k].clone() for k in self._IN_KEYS + ("action", "w")}
+            static["alpha_max"], static["static"] = s["alpha_max"], True
+            graphs, pool = [], None
+            torch.cuda.synchronize(self.device)
+            try:
+                for name in self._STAGES:
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg, pool=pool):
+                        getattr(self, name)(static)
+                    pool = cg.pool()
+                    graphs.append(cg)
+            except Exception as exc:   # capture is an optimisation of the torch side: say so and keep training eagerly
+                import warnings
+                warnings.warn(f"DiscreteSAC: CUDA-graph capture of the update failed ({exc}); updates stay eager")
+                self.cuda_graph = False
+                torch.cuda.synchronize(self.device)
+                return None
+            g = self._graph = {"key": key, "static": static, "graphs": graphs}
+        if key != g["key"]:
+            return None
+        st = g["static"]
+        for k in self._IN_KEYS + ("action", "w"):
+            st[k].copy_(s[k])
+        for i, cg in enumerate(g["graphs"]):
+            cg.replay()
+            self._reduce_after(i)
+        out = {k: st[k] for k in self._OUT_KEYS}
+        out["td_errors"] = st["td_errors"].clone()   # the caller keeps it past the next replay (priority update)
+        return out
 
     @torch.no_grad()
     def _soft_update(self, src: nn.Module, tgt: nn.Module) -> None:

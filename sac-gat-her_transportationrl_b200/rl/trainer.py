@@ -43,7 +43,7 @@ def default_config() -> Dict:
                 unassigned_penalty=1e4, max_steps=100, her_ratio=0.0, gat_layers=3, hidden_dim=256, embed_dim=256,
                 lr=1e-4, actor_lr=3e-5, critic_lr=1e-4, alpha_lr=1e-4, gamma=0.99, target_tau=0.001, grad_clip=1.0,
                 share_critic_encoder=False, seed=42, alpha_max=2.5, alpha_init=0.1, target_entropy_ratio=0.2,
-                precision="fp32", allow_tf32=False)
+                precision="fp32", allow_tf32=False, cuda_graph=True)
 
 
 class BatchedTrainer:
@@ -73,7 +73,8 @@ class BatchedTrainer:
                                  actor_lr=c["actor_lr"], critic_lr=c["critic_lr"], alpha_lr=c["alpha_lr"],
                                  grad_clip=c["grad_clip"], gamma=c["gamma"], target_tau=c["target_tau"],
                                  target_entropy_ratio=c["target_entropy_ratio"], alpha_init=c["alpha_init"],
-                                 share_critic_encoder=c["share_critic_encoder"], device=self.device)
+                                 share_critic_encoder=c["share_critic_encoder"], device=self.device,
+                                 cuda_graph=c["cuda_graph"])
         self.replay = DeviceReplay(int(c["buffer_size"]), net.num_nodes, net.num_edges, alpha=c["per_alpha"],
                                    beta=c["per_beta"], eps=c["per_eps"], device=self.device)
         self.gen = torch.Generator(device=self.device).manual_seed(c["seed"] * 7919 + self.rank)

@@ -102,6 +102,53 @@ def test_sac_update_matches_per_graph_formulas_and_checkpoint_roundtrip(b200env,
     assert float(other.log_alpha) == pytest.approx(float(agent.log_alpha))
 
 
+def test_sac_update_cuda_graph_replay_equals_eager(b200env, native_lib, sf_graph):
+    """``cuda_graph=True``: three eager updates, then the four stages are captured and replayed.  Same batches into
+    an eager twin -> same losses and parameters (Adam with device-side step counts rounds its bias corrections
+    differently, hence the tolerance); a batch of another size falls back to eager."""
+    rl = _rl()
+    net = b200env.Network(sf_graph)
+    dev = torch.device("cuda", 0)
+    agents = []
+    for graphed in (False, True):
+        torch.manual_seed(5)
+        agents.append(rl.DiscreteSAC(net, 4, 6, 32, 16, num_layers=3, lr=1e-3, grad_clip=1.0, share_critic_encoder=False,
+                                     device=dev, cuda_graph=graphed))
+    eager, graphed = agents
+    for a, b in zip(eager.actor.parameters(), graphed.actor.parameters()):
+        assert torch.equal(a, b)
+    g = torch.Generator(device=dev).manual_seed(11)
+
+    def make(B):
+        return {
+            "node_x": torch.rand(B, 24, 4, device=dev, generator=g), "edge_attr": torch.rand(B, 76, 6, device=dev, generator=g),
+            "action_mask": (torch.rand(B, 76, device=dev, generator=g) > 0.4).to(torch.uint8),
+            "next_node_x": torch.rand(B, 24, 4, device=dev, generator=g),
+            "next_edge_attr": torch.rand(B, 76, 6, device=dev, generator=g),
+            "next_action_mask": (torch.rand(B, 76, device=dev, generator=g) > 0.4).to(torch.uint8),
+            "action": torch.randint(0, 76, (B,), device=dev, generator=g), "reward": torch.rand(B, device=dev, generator=g),
+            "done": (torch.rand(B, device=dev, generator=g) > 0.8).float(),
+        }, torch.rand(B, device=dev, generator=g) + 0.5
+
+    for it in range(8):
+        batch, w = make(16 if it != 6 else 9)   # update 6 has another shape: eager on both
+        oe = eager.update(batch, weights=w, alpha_max=2.5)
+        og = graphed.update(batch, weights=w, alpha_max=2.5)
+        for k in ("critic_loss", "actor_loss", "alpha_loss", "alpha", "q_mean"):
+            assert float(og[k]) == pytest.approx(float(oe[k]), rel=2e-3, abs=2e-5), (it, k)
+        assert torch.allclose(og["td_errors"], oe["td_errors"], rtol=2e-3, atol=2e-5), it
+    assert graphed._graph is not None and len(graphed._graph["graphs"]) == 4 and eager._graph is None
+    # Adam's normalised step turns a rounding-level gradient difference on a near-zero gradient (the float atomics of
+    # index_add_ already differ from run to run) into a difference of up to one step size (lr) per update for that
+    # element; the losses above are the real check, the parameters must agree to within those few step sizes
+    for (n, a), b in zip(eager.actor.named_parameters(), graphed.actor.parameters()):
+        assert float((a - b).abs().max()) < 8 * 2e-3, n
+        if a.numel() >= 256:
+            assert float((a - b).norm() / a.norm()) < 0.05, n
+    for a, b in zip(eager.target1.parameters(), graphed.target1.parameters()):
+        assert torch.allclose(a, b, rtol=0, atol=2e-4)    # polyak with tau 0.005: 0.5 % of the critics' difference
+
+
 def test_batched_trainer_runs_episodes_updates_and_resets(b200env, native_lib, sf_graph):
     rl = _rl()
     cfg = dict(num_envs=32, assignment_iters=5, assignment_method="msa", buffer_size=4096, batch_start=64, update_every=2,

@@ -17,7 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1024)
     ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=24)   # past the CUDA-graph capture of the learner update (4th update)
     ap.add_argument("--iters", type=int, default=60)
     ap.add_argument("--method", default="cfw")
     ap.add_argument("--out", default="", help="also write the JSON line to this file (rank 0)")
