@@ -10,11 +10,12 @@ import b200env
 
 b200env.build_native()
 tr = b200env.rl.BatchedTrainer(b200env.load_sioux_falls(), dict(num_envs=1024, batch_start=256, buffer_size=100_000), device="cuda:0")
-tr.run(12)
+tr.run(24)   # past the CUDA-graph capture of the learner update (its 4th call)
 env, agent = tr.env, tr.agent
 
 
 def timed(fn, n=10):
+    fn()   # one untimed call: lazy initialisation, graph capture
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(n):
