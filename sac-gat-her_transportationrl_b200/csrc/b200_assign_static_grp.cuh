@@ -69,6 +69,11 @@ __device__ __forceinline__ void grp_bar(int threads)
     asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory");
 }
 
+// Registers: 7 CTAs of 3 warps put 6 warps on one of the SM's four sub-partitions (16 K registers each), so a thread
+// may use at most 16384 / (6 x 32) = 85 -> 80 registers; ptxas derives that from the bounds below (96 or 88 registers
+// drop the occupancy to 6 CTAs per SM and the 4096-scenario launch to two waves: measured 0.44-0.46 ms against 0.33).
+// Tried and dropped: keeping the tree (parent, in-link, children counts) in registers until the Kahn scan and packing
+// parent | slot | sum into one word - 15 % fewer shared-memory wavefronts, but more instructions and spills: 0.36 ms.
 template <class T>
 __global__ void __launch_bounds__(GrpShape<T>::TH, 65536 / (GrpShape<T>::TH * 96) > 0 ? 65536 / (GrpShape<T>::TH * 96) : 1)
     assign_static_grp_kernel(const Params p)
