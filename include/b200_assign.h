@@ -105,7 +105,8 @@ int b200_assign_launches(const b200_graph *g);
  * thread-block cluster size (1 = one CTA per scenario), cfg[2] = 1 when iterations after the first
  * warm-started their shortest paths from the previous trees, cfg[3] = warps per CTA, cfg[4] = 1 when
  * shortest paths came from the contraction-hierarchy sweeps (exactly summable fp32 costs) rather
- * than from label correcting, cfg[5..7] reserved (0).  Parity tests use it to prove that the path
+ * than from label correcting, 2 when additionally the grouped variant of the network-specialised
+ * kernel ran (several scenarios per group of warps, no idle origin lanes), cfg[5..7] reserved (0).  Parity tests use it to prove that the path
  * they mean to cover (cluster mode, warm start, hierarchy) is the one that ran. */
 int b200_assign_last_config(const b200_graph *g, int32_t cfg[8]);
 /* Host-only self-check of the contraction-hierarchy planner behind the general fused kernel
