@@ -6,6 +6,7 @@ CPU fallback - every compute entry point raises if the library (or a CUDA device
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import shutil
 import subprocess
@@ -54,8 +55,15 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
+def _obj_dir() -> str:
+    """csrc/_obj for the product build; a tuning build (B200_NVCC_EXTRA) keeps its objects apart so that they can
+    never be linked into the product library by a later incremental build"""
+    extra = os.environ.get("B200_NVCC_EXTRA", "").strip()
+    return os.path.join(CSRC, "_obj" if not extra else "_obj_" + hashlib.sha1(extra.encode()).hexdigest()[:8])
+
+
 def _obj_path(src: str) -> str:
-    return os.path.join(CSRC, "_obj", os.path.splitext(src)[0] + ".o")
+    return os.path.join(_obj_dir(), os.path.splitext(src)[0] + ".o")
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -63,7 +71,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     One object per source, compiled in parallel, then linked; objects live in csrc/_obj/."""
     if not force and not _stale():
         return LIB_PATH
-    os.makedirs(os.path.join(CSRC, "_obj"), exist_ok=True)
+    os.makedirs(_obj_dir(), exist_ok=True)
     compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
     compile_flags += os.environ.get("B200_NVCC_EXTRA", "").split()  # kernel-tuning experiments (-DB200_STATIC_MINB=..)
     api = os.path.join("..", "..", "include", "b200_assign.h")

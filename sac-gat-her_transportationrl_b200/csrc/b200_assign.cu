@@ -399,6 +399,35 @@ __device__ int warp_sssp_bf(const Cta<REAL> &c, const Params &p, int origin, con
     return 1;
 }
 
+#ifdef B200_PHASE_TIMING
+// tuning builds only (B200_NVCC_EXTRA=-DB200_PHASE_TIMING): SM clocks CTA 0 spends per phase, summed over iterations
+__device__ unsigned long long g_phase_clocks[8], g_sub_clocks[8];
+__device__ int g_dbg_flags;   // bit 0: skip the link-load atomics of the chain walk (timing experiment, wrong results)
+#define B200_PHASE_MARK(i)                                                         \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                     \
+        const long long now_ = clock64();                                          \
+        g_phase_clocks[i] += (unsigned long long)(now_ - mark_);                   \
+        mark_ = now_;                                                              \
+    }
+// inside one origin solve: warp 0 of CTA 0
+#define B200_SUB_BEGIN long long sub_ = clock64();
+#define B200_SUB_MARK(i)                                                           \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                     \
+        const long long now_ = clock64();                                          \
+        g_sub_clocks[i] += (unsigned long long)(now_ - sub_);                      \
+        sub_ = now_;                                                               \
+    }
+#define B200_DBG_SKIP_AUX (g_dbg_flags & 1)
+#define B200_DBG_COUNT(i, n) if (blockIdx.x == 0 && threadIdx.x == 0) g_sub_clocks[i] += (n);
+#else
+#define B200_PHASE_MARK(i)
+#define B200_SUB_BEGIN
+#define B200_SUB_MARK(i)
+#define B200_DBG_SKIP_AUX 0
+#define B200_DBG_COUNT(i, n)
+#endif
+
+
 // Down stream of the hierarchy (b200_cch.cu): batches of a header row + D edge rows, all of one shape, so
 // the loop body is branch-free; the words of the NEXT batch are fetched into registers before the current
 // one is relaxed, which hides the latency of whatever level of the memory hierarchy holds the table.
@@ -440,6 +469,7 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
     const CchParams &h = p.cch;
     const int lane = threadIdx.x & 31, N = c.N;
     double *dist = s.dist;
+    B200_SUB_BEGIN
     for (int v = lane; v < h.slots; v += 32) dist[v] = (v == origin) ? 0.0 : B200_INF_F64;
     {
         const double *__restrict__ wu = c.wu;
@@ -459,6 +489,7 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
         }
     }
     __syncwarp();
+    B200_SUB_MARK(0)   // label init + up phase
     switch (h.D) {
         case 2: cch_down_sweep<2>(h.dn_rows, h.dn_batches, dist, c.wd); break;
         case 3: cch_down_sweep<3>(h.dn_rows, h.dn_batches, dist, c.wd); break;
@@ -468,6 +499,7 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
         default: cch_down_sweep<8>(h.dn_rows, h.dn_batches, dist, c.wd); break;
     }
     __syncwarp();
+    B200_SUB_MARK(1)   // down sweep
     unsigned mx = 0;
     for (int v = lane; v < N; v += 32) {
         const unsigned hi = (unsigned)__double2hiint(dist[v]);
@@ -494,6 +526,7 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
         if (v < N) s.pk[v] = (uint16_t)((v != origin && dv < B200_INF_F64) ? bk : kNoPk);
     }
     __syncwarp();
+    B200_SUB_MARK(2)   // exactness check + predecessor selection
     return capped;
 }
 
@@ -588,6 +621,7 @@ __device__ double warp_aon_chain(Cta<REAL> &c, const Params &p, int slot, int or
     unsigned *word = (unsigned *)s.dist;   // dist is dead once pk is chosen
     int *auxq = (int *)c.aux;
     const REAL *q = (const REAL *)p.od_q;
+    B200_SUB_BEGIN
     for (int v = lane; v < N; v += 32) word[v] = 0u;
     __syncwarp();
     const int jd1 = __ldg(p.od_ptr + slot + 1);
@@ -610,6 +644,10 @@ __device__ double warp_aon_chain(Cta<REAL> &c, const Params &p, int slot, int or
         count += __popc(m);
     }
     __syncwarp();
+    B200_SUB_MARK(3)   // demand scatter, children counts, leaf list
+    // Tried and dropped: the tree parent packed into the word as well (the delivering atomic then returns where to
+    // go next: one dependent shared-memory operation per step instead of three) - no gain, the walk is bound by its
+    // ~70 serial steps per origin (tree height) at ~6 active lanes, not by the latency of a step.
     int next = lane, v = -1;
     unsigned sv = 0u;
     for (;;) {
@@ -619,9 +657,16 @@ __device__ double warp_aon_chain(Cta<REAL> &c, const Params &p, int slot, int or
             next += 32;
         }
         if (!__any_sync(FULL, v >= 0)) break;
+#ifdef B200_PHASE_TIMING
+        {
+            const int act_ = __popc(__ballot_sync(FULL, v >= 0));   // every lane takes part in the ballot
+            B200_DBG_COUNT(5, 1)
+            B200_DBG_COUNT(6, act_)
+        }
+#endif
         if (v >= 0) {
             const int k = s.pk[v], u = in_src[k];
-            if (sv != 0u) atomicAdd(&auxq[in_eid[k]], (int)sv);
+            if (sv != 0u && !B200_DBG_SKIP_AUX) atomicAdd(&auxq[in_eid[k]], (int)sv);
             const unsigned old = atomicAdd(&word[u], sv - kChild);
             // the last child to arrive carries the parent's completed subtree sum upwards
             const bool last = (old >> 28) == 1u && u != origin;
@@ -629,6 +674,7 @@ __device__ double warp_aon_chain(Cta<REAL> &c, const Params &p, int slot, int or
             v = last ? u : -1;
         }
     }
+    B200_SUB_MARK(4)   // chain walk
     return un;
 }
 
@@ -986,11 +1032,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
         if (threadIdx.x == 0) { flag_s[0] = 0; flag_s[1] = 0; }
         __syncthreads();
         cta_costs_from_flow<REAL>(c, p, dmg_b);
+#ifdef B200_PHASE_TIMING
+        long long mark_ = clock64();
+#endif
         for (int it = 0; it < p.K; ++it) {
             for (int e = threadIdx.x; e < c.E; e += blockDim.x) c.aux[e] = 0;
             if (threadIdx.x == 0) *un_s = 0.0;
             __syncthreads();   // (neighbours finished pulling last iteration's loads before its last cluster barrier)
+            B200_PHASE_MARK(0)
             if (CCH) cta_customize<REAL>(c, p);
+            B200_PHASE_MARK(1)
             double un = 0.0;
             int capped = 0;
             for (int s = rank * W + warp; s < p.O; s += C * W) {
@@ -1010,16 +1061,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
             un = warp_sum_f64(un);
             if (lane == 0 && un != 0.0) atomicAdd(un_s, un);
             if (__any_sync(0xffffffffu, capped) && lane == 0) flag_s[1] = 1;
+            B200_PHASE_MARK(2)   // warp 0's own origins
             __syncthreads();
+            B200_PHASE_MARK(3)   // waiting for the CTA's other warps
             if (C > 1) {
                 cluster.sync();   // every CTA's partial loads are complete
+                B200_PHASE_MARK(4)
                 if (c.intq) cluster_combine<REAL, true>(c, cluster, un_s, flag_s);
                 else cluster_combine<REAL, false>(c, cluster, un_s, flag_s);
+                B200_PHASE_MARK(5)
             }
             int nan_seen = 0;
             cta_update<REAL>(c, p, dmg_b, it, dprev_b, it == p.K - 1, p.gap + b, &nan_seen);
             if (nan_seen) flag_s[0] = 1;
             __syncthreads();
+            B200_PHASE_MARK(6)
         }
         const double un_final = *un_s;
         cta_tstt<REAL>(c, p, c.aux, un_final, p.tstt + b);
@@ -1229,6 +1285,27 @@ int b200_pick_warps_cch(b200_graph *g)
     g->smem_cch = best_smem;
     return best_w;
 }
+
+#ifdef B200_PHASE_TIMING
+extern "C" int b200_debug_flags(int flags)
+{
+    B200_CUDA(cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof(int)));
+    return 0;
+}
+
+extern "C" int b200_debug_phase_clocks(unsigned long long out[16], int reset)
+{
+    B200_CUDA(cudaDeviceSynchronize());
+    B200_CUDA(cudaMemcpyFromSymbol(out, g_phase_clocks, sizeof(unsigned long long) * 8));
+    B200_CUDA(cudaMemcpyFromSymbol(out + 8, g_sub_clocks, sizeof(unsigned long long) * 8));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        B200_CUDA(cudaMemcpyToSymbol(g_phase_clocks, z, sizeof(z)));
+        B200_CUDA(cudaMemcpyToSymbol(g_sub_clocks, z, sizeof(z)));
+    }
+    return 0;
+}
+#endif
 
 #define B200_PREC_OK(prec) B200_REQUIRE((prec) == B200_F32 || (prec) == B200_F64, "prec must be B200_F32 or B200_F64")
 
