@@ -338,8 +338,10 @@ __device__ void warp_select_pred(const Cta<REAL> &c, int origin, const WarpScrat
 // Customization, once per (scenario, iteration), all warps of the CTA: every filled edge starts from
 // its own link cost (+inf for a pure shortcut), then the rows of each level - 32 edges with their
 // lower triangles, most triangles first - are dealt to the warps round-robin; a CTA barrier separates
-// the levels (the two lower edges of a triangle are final one level earlier).
-template <typename REAL>
+// the levels (the two lower edges of a triangle are final one level earlier).  A warp goes straight to
+// its rows (per-level row ranges, per-row table offsets) and fetches four triangle words ahead of the
+// shared-memory reads they address: the table (Chicago-Sketch-size: 200 KB) lives in L2.
+template <typename REAL, int G>   // G: triangle words in flight per lane (8 when registers allow, else 4)
 __device__ void cta_customize(const Cta<REAL> &c, const Params &p)
 {
     const CchParams &h = p.cch;
@@ -349,24 +351,37 @@ __device__ void cta_customize(const Cta<REAL> &c, const Params &p)
         *c.wpos((int)(wi & 0xffffu)) = slot == 0xffff ? B200_INF_F64 : c.w[slot];
     }
     const int W = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int off = 0, turn = 0;
-    for (int r = 0; r < h.cz_rows; ++r) {
-        const uint32_t desc = __ldg(h.cz_desc + r);
-        const int T = (int)(desc & 0xffffu);
-        if (desc & 0x10000u) { __syncthreads(); turn = 0; }
-        if (turn == warp) {
-            const uint32_t *row = h.cz_tab + off;
-            double *dst = c.wpos((int)__ldg(row + lane));
+    auto relax = [&](double acc, uint32_t tri) {
+        const double cand = *c.wpos((int)(tri & 0xffffu)) + *c.wpos((int)(tri >> 16));
+        return cand < acc ? cand : acc;
+    };
+    const uint32_t inf_pair = (uint32_t)(h.wd + h.wu) * 0x10001u;   // both halves point at the +inf slot
+    for (int L = 0; L < h.cz_levels; ++L) {
+        __syncthreads();
+        const int r0 = (int)__ldg(h.cz_lvl + L), r1 = (int)__ldg(h.cz_lvl + L + 1);
+        for (int r = r0 + warp; r < r1; r += W) {
+            const uint32_t desc = __ldg(h.cz_desc + r);
+            const int T = (int)(desc & 0xfffu);
+            const uint32_t *row = h.cz_tab + (size_t)(desc >> 12) * 32 + lane;
+            double *dst = c.wpos((int)__ldg(row));
+            row += 32;
             double acc = *dst;
-            for (int t = 0; t < T; ++t) {
-                const uint32_t tri = __ldg(row + 32 * (t + 1) + lane);
-                const double cand = *c.wpos((int)(tri & 0xffffu)) + *c.wpos((int)(tri >> 16));
-                acc = cand < acc ? cand : acc;
+            // groups of G triangle words, the next group in flight while this one is relaxed (a row of the dense top
+            // of the hierarchy has dozens of triangles per edge and is the critical path of its level)
+            uint32_t cur[G], nxt[G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) cur[i] = i < T ? __ldg(row + 32 * i) : inf_pair;
+            for (int t = 0; t < T; t += G) {
+                row += 32 * G;
+#pragma unroll
+                for (int i = 0; i < G; ++i) nxt[i] = t + G + i < T ? __ldg(row + 32 * i) : inf_pair;
+#pragma unroll
+                for (int i = 0; i < G; ++i) acc = relax(acc, cur[i]);
+#pragma unroll
+                for (int i = 0; i < G; ++i) cur[i] = nxt[i];
             }
             *dst = acc;
         }
-        off += 32 * (T + 1);
-        turn = turn + 1 == W ? 0 : turn + 1;
     }
     __syncthreads();
 }
@@ -511,6 +526,8 @@ __device__ int warp_sssp_cch(const Cta<REAL> &c, const Params &p, int slot, int 
     // "tail | CSC slot" per block of 32 nodes, ascending tail, so "<=" leaves the largest u among equals)
     const double *__restrict__ w = c.w;
     const uint32_t *sp = h.sel_rows + lane;
+    // (tried: fetching the next block's rows ahead like the down stream does - no gain on Chicago-Sketch-size and
+    // spills under the 64-register bound of the two-CTA instantiation)
     for (int v = lane; v < ((N + 31) & ~31); v += 32, sp += h.SD * 32) {
         const double dv = v < N ? dist[v] : B200_INF_F64;
         int bk = kNoPk;
@@ -1040,7 +1057,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, MINB) assign_fused_kernel(Para
             if (threadIdx.x == 0) *un_s = 0.0;
             __syncthreads();   // (neighbours finished pulling last iteration's loads before its last cluster barrier)
             B200_PHASE_MARK(0)
-            if (CCH) cta_customize<REAL>(c, p);
+            if (CCH) cta_customize<REAL, (MINB == 1 ? 8 : 4)>(c, p);
             B200_PHASE_MARK(1)
             double un = 0.0;
             int capped = 0;
@@ -1121,10 +1138,10 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
     if (g->cch_ok) {
         p.cch.dn_rows = g->cch_dn_rows; p.cch.up_rows = g->cch_up_rows; p.cch.sel_rows = g->cch_sel_rows;
         p.cch.up_off = g->cch_up_off; p.cch.cz_init = g->cch_cz_init;
-        p.cch.cz_desc = g->cch_cz_desc; p.cch.cz_tab = g->cch_cz_tab;
+        p.cch.cz_desc = g->cch_cz_desc; p.cch.cz_tab = g->cch_cz_tab; p.cch.cz_lvl = g->cch_cz_lvl;
         p.cch.F = g->cch_F; p.cch.wd = g->cch_wd; p.cch.wu = g->cch_wu; p.cch.slots = g->cch_slots;
         p.cch.dn_batches = g->cch_dn_batches; p.cch.D = g->cch_D; p.cch.SD = g->cch_SD;
-        p.cch.cz_rows = g->cch_cz_rows; p.cch.wmode = g->cch_wmode;
+        p.cch.cz_rows = g->cch_cz_rows; p.cch.cz_levels = g->cch_cz_levels; p.cch.wmode = g->cch_wmode;
         p.cch.topo_bytes = g->o16_out_ptr * 2;   // in_ptr | in_src | in_eid: the out-link arrays are not needed
         union { double d; unsigned long long u; } lim;
         lim.d = g->cch_exact_limit;

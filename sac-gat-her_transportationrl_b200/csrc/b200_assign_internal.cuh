@@ -85,9 +85,9 @@ struct SmallOffsets {
 
 // contraction-hierarchy tables of the general fused kernel (b200_cch.cu), device pointers
 struct CchParams {
-    const uint32_t *dn_rows, *up_rows, *sel_rows, *up_off, *cz_init, *cz_desc, *cz_tab;
+    const uint32_t *dn_rows, *up_rows, *sel_rows, *up_off, *cz_init, *cz_desc, *cz_tab, *cz_lvl;
     double *ws;            // per-CTA weight workspace in HBM (the part of W outside shared memory)
-    int F, wd, wu, slots, dn_batches, D, SD, cz_rows;
+    int F, wd, wu, slots, dn_batches, D, SD, cz_rows, cz_levels;
     int topo_bytes;        // staged part of the 16-bit topology blob: in_ptr | in_src | in_eid
     int wmode;             // 0: W in HBM/L2, 1: down region in shared memory, 2: all of W in shared memory
     int ws_stride;         // doubles per CTA in ws

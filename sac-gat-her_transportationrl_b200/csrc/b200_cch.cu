@@ -216,7 +216,9 @@ int up(T **dst, const std::vector<T> &src)
 // Everything the kernel reads, as host vectors (uploaded by b200_cch_prepare, replayed on the host by
 // b200_cch_host_sssp).
 struct Tables {
-    std::vector<uint32_t> dn_rows, up_rows, up_off, sel_rows, cz_init, cz_desc, cz_tab;   // up_off[O + 1]: first PAIR of origin slot s
+    // up_off[O + 1]: first PAIR of origin slot s; cz_lvl[L]: first row of customization level L (+ end);
+    // cz_desc[r] = triangles per edge of row r (12 bits) | first word of the row in cz_tab / 32 << 12
+    std::vector<uint32_t> dn_rows, up_rows, up_off, sel_rows, cz_init, cz_desc, cz_tab, cz_lvl;
     int F = 0, wd = 0, wu = 0, slots = 0, tris = 0, dn_batches = 0, D = 0, SD = 0;
 };
 
@@ -306,7 +308,8 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
         lvl[e] = l;
         max_lvl = std::max(max_lvl, l);
     }
-    for (int L = 1; L <= max_lvl; ++L) {   // desc: T | 0x10000 if a CTA barrier must precede the row
+    for (int L = 1; L <= max_lvl; ++L) {   // rows of one level are independent; a CTA barrier separates the levels
+        T.cz_lvl.push_back((uint32_t)T.cz_desc.size());
         std::vector<int> es;
         for (int e = 0; e < P.F; ++e)
             if (lvl[e] == L) es.push_back(e);
@@ -314,7 +317,8 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
         for (size_t i = 0; i < es.size(); i += 32) {
             const size_t j = std::min(es.size(), i + 32);
             const int nt = (int)P.tris[es[i]].size();
-            T.cz_desc.push_back((uint32_t)nt | (i == 0 ? 0x10000u : 0u));
+            if (nt > 4095 || T.cz_tab.size() / 32 >= (1u << 20)) return false;   // descriptor fields
+            T.cz_desc.push_back((uint32_t)nt | (uint32_t)(T.cz_tab.size() / 32) << 12);
             for (int l = 0; l < 32; ++l) T.cz_tab.push_back(i + l < j ? (uint32_t)pos[es[i + l]] : DUMMY);
             for (int t = 0; t < nt; ++t)
                 for (int l = 0; l < 32; ++l) {
@@ -328,6 +332,7 @@ bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, in
                 }
         }
     }
+    T.cz_lvl.push_back((uint32_t)T.cz_desc.size());
     T.dn_rows = std::move(D.rows);
     T.F = P.F; T.wd = D.wlen; T.wu = nu; T.slots = D.slots; T.dn_batches = D.batches; T.D = D.D;
     return true;
@@ -367,9 +372,9 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
         const uint32_t wi = T.cz_init[e];
         W[wi & 0xffffu] = (wi >> 16) == 0xffffu ? INF : cost[in_eid[wi >> 16]];
     }
-    size_t off = 0;
     for (size_t r = 0; r < T.cz_desc.size(); ++r) {
-        const int nt = (int)(T.cz_desc[r] & 0xffffu);
+        const int nt = (int)(T.cz_desc[r] & 0xfffu);
+        const size_t off = (size_t)(T.cz_desc[r] >> 12) * 32;
         std::vector<double> acc(32);
         for (int l = 0; l < 32; ++l) {
             acc[l] = W[T.cz_tab[off + l]];
@@ -380,7 +385,6 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
             }
         }
         for (int l = 0; l < 32; ++l) W[T.cz_tab[off + l]] = acc[l];
-        off += 32 * (size_t)(nt + 1);
     }
     std::vector<double> d(T.slots, INF);
     d[origin] = 0.0;
@@ -423,7 +427,8 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
     int rc;
     if ((rc = up(&g->cch_dn_rows, T.dn_rows)) || (rc = up(&g->cch_up_rows, T.up_rows)) ||
         (rc = up(&g->cch_sel_rows, T.sel_rows)) || (rc = up(&g->cch_up_off, T.up_off)) ||
-        (rc = up(&g->cch_cz_init, T.cz_init)) || (rc = up(&g->cch_cz_desc, T.cz_desc)) || (rc = up(&g->cch_cz_tab, T.cz_tab)))
+        (rc = up(&g->cch_cz_init, T.cz_init)) || (rc = up(&g->cch_cz_desc, T.cz_desc)) || (rc = up(&g->cch_cz_tab, T.cz_tab)) ||
+        (rc = up(&g->cch_cz_lvl, T.cz_lvl)))
         return rc;
     g->cch_D = T.D;
     g->cch_SD = T.SD;
@@ -433,6 +438,7 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
     g->cch_slots = T.slots;
     g->cch_dn_batches = T.dn_batches;
     g->cch_cz_rows = (int)T.cz_desc.size();
+    g->cch_cz_levels = (int)T.cz_lvl.size() - 1;
     g->cch_tris = T.tris;
     int e2 = 0;
     frexp((double)g->min_t0, &e2);
@@ -444,7 +450,7 @@ int b200_cch_prepare(b200_graph *g, const int32_t *in_ptr, const int32_t *in_src
 void b200_cch_destroy(b200_graph *g)
 {
     void *ptrs[] = {g->cch_dn_rows, g->cch_up_rows, g->cch_sel_rows, g->cch_up_off,
-                    g->cch_cz_init, g->cch_cz_desc, g->cch_cz_tab, g->cch_ws};
+                    g->cch_cz_init, g->cch_cz_desc, g->cch_cz_tab, g->cch_cz_lvl, g->cch_ws};
     for (void *p : ptrs)
         if (p) cudaFree(p);
 }
