@@ -45,7 +45,7 @@ struct Cta {
     // cch_wd and wu[pos - cch_wd] from there on (the +inf and dummy slots follow the up region)
     double *wd, *wu;
     int cch_wd;
-    bool lean;   // per-warp scratch without the second queue / counters (warp_offsets)
+    int lean;    // per-warp scratch without the second queue / counters (warp_offsets)
     int topo_bytes;   // staged part of the topology blob
 
     // link load of link e as REAL, whatever the accumulation type
@@ -58,8 +58,8 @@ struct Cta {
         const size_t w_smem = !cch ? 0 : (wmode == 2 ? (size_t)(p.cch.wd + p.cch.wu + 2) * 8 : wmode == 1 ? (size_t)p.cch.wd * 8 : 0);
         topo_bytes = cch ? p.cch.topo_bytes : p.topo16_bytes;
         SmemLayout L = make_layout(p.N, p.E, topo_bytes, warps, (int)sizeof(REAL), alias_cnt, cch ? p.cch.slots : 0,
-                                   w_smem, cch && p.kahn_pack);
-        lean = cch && p.kahn_pack;
+                                   w_smem, (cch && p.kahn_pack) ? 1 + p.cch.leaf_alias : 0);
+        lean = (cch && p.kahn_pack) ? 1 + p.cch.leaf_alias : 0;
         if (cch) {
             double *ws_cta = p.cch.ws + (size_t)blockIdx.x * p.cch.ws_stride;
             double *sm = (double *)(smem + L.off_cchw);
@@ -1141,7 +1141,7 @@ Params base_params(const b200_graph *g, int B, int prec, double alpha, double be
         p.cch.cz_desc = g->cch_cz_desc; p.cch.cz_tab = g->cch_cz_tab; p.cch.cz_lvl = g->cch_cz_lvl;
         p.cch.F = g->cch_F; p.cch.wd = g->cch_wd; p.cch.wu = g->cch_wu; p.cch.slots = g->cch_slots;
         p.cch.dn_batches = g->cch_dn_batches; p.cch.D = g->cch_D; p.cch.SD = g->cch_SD;
-        p.cch.cz_rows = g->cch_cz_rows; p.cch.cz_levels = g->cch_cz_levels; p.cch.wmode = g->cch_wmode;
+        p.cch.cz_rows = g->cch_cz_rows; p.cch.cz_levels = g->cch_cz_levels; p.cch.wmode = g->cch_wmode; p.cch.leaf_alias = g->cch_leaf_alias;
         p.cch.topo_bytes = g->o16_out_ptr * 2;   // in_ptr | in_src | in_eid: the out-link arrays are not needed
         union { double d; unsigned long long u; } lim;
         lim.d = g->cch_exact_limit;
@@ -1278,13 +1278,14 @@ int b200_pick_warps_cch(b200_graph *g)
     const int forced_w = getenv("B200_WARPS") ? atoi(getenv("B200_WARPS")) : 0;
     const int forced_m = getenv("B200_CCH_W") ? atoi(getenv("B200_CCH_W")) : -1;
     double best_score = -1.0;
-    int best_w = -1, best_m = 0;
+    int best_w = -1, best_m = 0, best_la = 0;
     size_t best_smem = 0;
     for (int mode = 2; mode >= 0; --mode) {
         if (forced_m >= 0 && mode != forced_m) continue;
         const size_t wb = mode == 2 ? (size_t)(g->cch_wd + g->cch_wu + 2) * 8 : mode == 1 ? (size_t)g->cch_wd * 8 : 0;
+        for (int la = 0; la <= (g->kahn_pack ? 1 : 0); ++la)   // leaf list inside dist[]: only if it scores higher
         for (int w = kMinWarps; w <= kMaxWarps; ++w) {
-            SmemLayout L = make_layout(g->N, g->E, g->o16_out_ptr * 2, w, 4, true, g->cch_slots, wb, g->kahn_pack != 0);
+            SmemLayout L = make_layout(g->N, g->E, g->o16_out_ptr * 2, w, 4, true, g->cch_slots, wb, g->kahn_pack ? 1 + la : 0);
             if (L.total > kSmemLimit) break;
             if (forced_w && w != forced_w) continue;
             const int O = std::max(g->O, 1);
@@ -1292,12 +1293,13 @@ int b200_pick_warps_cch(b200_graph *g)
             const int ctas = std::min<int>((int)((228 * 1024) / (L.total + 1024)), std::min(32, 64 / w));
             // resident warps, with a premium for weights in shared memory: every origin gathers from the whole
             // down region, and the up phase is a chain of dependent reads (L2 latency per ancestor otherwise)
-            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 1.3 : mode == 1 ? 1.15 : 1.0);
-            if (score > best_score + 1e-9) { best_score = score; best_w = w; best_m = mode; best_smem = L.total; }
+            const double score = eff * w * std::max(ctas, 1) * (mode == 2 ? 1.3 : mode == 1 ? 1.15 : 1.0) * (la ? 0.97 : 1.0);
+            if (score > best_score + 1e-9) { best_score = score; best_w = w; best_m = mode; best_smem = L.total; best_la = la; }
         }
     }
     if (best_w < 0) return -1;
     g->warps_cch = best_w;
+    g->cch_leaf_alias = best_la;
     g->cch_wmode = best_m;
     g->smem_cch = best_smem;
     return best_w;

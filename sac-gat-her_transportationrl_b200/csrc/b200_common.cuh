@@ -105,7 +105,7 @@ struct b200_graph {
     // with their lower triangles); W positions: [0, cch_wd) down edges + one zero-weight slot, then cch_wu up-region entries,
     // then the +inf and the write-only dummy slot.  cch_ws: per-CTA weight workspace in HBM for the
     // part of W that does not fit shared memory, grown on demand like tree_ws.
-    int cch_ok, cch_F, cch_wd, cch_wu, cch_slots, cch_dn_batches, cch_cz_rows, cch_cz_levels, cch_tris, cch_wmode;
+    int cch_ok, cch_F, cch_wd, cch_wu, cch_slots, cch_dn_batches, cch_cz_rows, cch_cz_levels, cch_tris, cch_wmode, cch_leaf_alias;
     double cch_exact_limit;
     uint32_t *cch_dn_rows, *cch_up_rows, *cch_sel_rows, *cch_up_off, *cch_cz_init, *cch_cz_desc, *cch_cz_tab, *cch_cz_lvl;
     int cch_D, cch_SD;   // edge rows per down batch, rows per block of the select stream
