@@ -48,9 +48,10 @@ struct Plan {
 
 inline uint64_t key(int u, int x) { return ((uint64_t)(uint32_t)u << 32) | (uint32_t)x; }
 
-// Elimination in rounds of independent low-degree nodes (degree <= max(min degree, 2)): keeps the
-// elimination tree shallow, which is what bounds the number of levels of the down sweep.
-Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
+// Elimination in rounds of independent low-degree nodes (degree <= max(min degree, 2) + slack): keeps the
+// elimination tree shallow, which is what bounds the number of levels of the down sweep.  slack trades rounds
+// (= levels) against fill; build_tables tries a few values and keeps the cheapest sweep.
+Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src, int slack)
 {
     Plan P;
     P.N = N;
@@ -79,7 +80,7 @@ Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src)
         int mind = 1 << 30;
         for (int v = 0; v < N; ++v)
             if (alive[v]) { cand.push_back(v); mind = std::min(mind, (int)adj[v].size()); }
-        const int thr = std::max(mind, 2);
+        const int thr = std::max(mind, 2) + slack;
         std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return adj[a].size() < adj[b].size(); });
         std::vector<int> chosen;
         std::vector<char> blocked(N, 0);
@@ -223,15 +224,41 @@ struct Tables {
 };
 
 // false: the network is outside the 16-bit limits of the tables
-bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, int O, const int32_t *origins, Tables &T)
+// model_origins: origin count the plan search assumes (the host replay of one origin passes the network's scale)
+bool build_tables(int N, int E, const int32_t *in_ptr, const int32_t *in_src, int O, const int32_t *origins, Tables &T,
+                  int model_origins = 0)
 {
     if (N >= 65000 || E >= 65000) return false;
-    Plan P = make_plan(N, E, in_ptr, in_src);
+    // Plan search: elimination slack x edge rows per batch.  Cost model from the phase timings of the kernel
+    // (tools/phase_timing.py): a down batch costs a warp ~300 clocks of dependent latency + ~55 per edge row, every
+    // origin runs all batches (16 warps share the origins), a lower triangle costs the CTA ~9 clocks of customization.
+    const char *force_d = getenv("B200_CCH_D"), *force_slack = getenv("B200_CCH_SLACK");   // tuning: force either
+    Plan P;
     DownLayout D;
-    for (int d : {2, 3, 4, 5, 6, 8}) {   // fewest rows wins (a row costs the same whatever it holds)
-        DownLayout c = down_layout(P, d);
-        if (D.batches == 0 || c.batches * (1 + c.D) < D.batches * (1 + D.D)) D = std::move(c);
+    double best_cost = -1.0;
+    for (int slack = 0; slack <= 2; ++slack) {
+        if (force_slack && atoi(force_slack) != slack) continue;
+        Plan cand = make_plan(N, E, in_ptr, in_src, slack);
+        size_t tr = 0;
+        for (auto &t : cand.tris) tr += t.size();
+        DownLayout best_d;
+        double cost_d = -1.0;
+        for (int d : {2, 3, 4, 5, 6, 8}) {
+            if (force_d && atoi(force_d) != d) continue;
+            DownLayout c = down_layout(cand, d);
+            const double cost = (double)std::max(model_origins > 0 ? model_origins : O, 1) * c.batches * (300.0 + 55.0 * d) / 16.0 + 9.0 * (double)tr;
+            if (getenv("B200_CCH_DEBUG"))
+                fprintf(stderr, "[b200 cch] slack %d D=%d: %d batches, %d slots; %d filled edges, %zu triangles; model %.0f\n",
+                        slack, d, c.batches, c.slots, cand.F, tr, cost);
+            if (cost_d < 0.0 || cost < cost_d) { cost_d = cost; best_d = std::move(c); }
+        }
+        if (cost_d >= 0.0 && (best_cost < 0.0 || cost_d < best_cost * 0.98)) {   // a new slack must win by 2 %
+            best_cost = cost_d;
+            P = std::move(cand);
+            D = std::move(best_d);
+        }
     }
+    if (best_cost < 0.0) return false;
     // up region: out-edges to higher-ranked heads, CSR by tail
     std::vector<int> pos(P.F, -1);
     std::vector<std::vector<int>> uo(N);
@@ -364,7 +391,7 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
     make_csc(N, E, row, col, in_ptr, in_src, in_eid);
     Tables T;
     const int32_t one_origin[1] = {origin};
-    if (!build_tables(N, E, in_ptr.data(), in_src.data(), 1, one_origin, T)) { b200_set_error("network too large for the hierarchy tables"); return B200_EUNSUPPORTED; }
+    if (!build_tables(N, E, in_ptr.data(), in_src.data(), 1, one_origin, T, std::max(1, N / 4))) { b200_set_error("network too large for the hierarchy tables"); return B200_EUNSUPPORTED; }
     const double INF = INFINITY;
     std::vector<double> W((size_t)T.wd + T.wu + 2, 0.0);   // position wd - 1 keeps 0.0: the zero-weight slot
     W[T.wd + T.wu] = INF;
