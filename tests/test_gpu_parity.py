@@ -697,6 +697,12 @@ def test_static_kernel_hierarchy_sweeps_equal_gauss_seidel_and_oracle(b200env, n
     # undamaged network, free-flow ties everywhere (iteration 0 of a cold start)
     z = np.zeros((2, 76), np.uint8)
     assert np.array_equal(_assign(cch, z, 20, "fw")["flow"], _assign(gs, z, 20, "fw")["flow"])
+    # BASELINE config 2 also names K = 50: grouped kernel vs the C oracle, bit for bit
+    a50 = _assign(cch, masks[:64], 50, "fw")
+    assert cch.last_config["cch"] == 2
+    for s in (0, 31, 63):
+        o = sf_oracle.assign(masks[s], None, 50, "fw")
+        assert np.array_equal(a50["flow"][s], o["flow"]) and a50["tstt"][s] == o["tstt"], s
     # grouped kernel: a batch that is not a multiple of the group, and rows switched off by `active`
     # (those keep every output they had)
     for n in (1, 3, 5, 7):
