@@ -469,7 +469,16 @@ __device__ __forceinline__ void cch_down_sweep(const uint32_t *__restrict__ rows
         for (int i = 0; i < D; ++i) cand[i] = dist[cur[i + 1] & 0xffffu] + wd[cur[i + 1] >> 16];
 #pragma unroll
         for (int i = 0; i < D; ++i) best = cand[i] < best ? cand[i] : best;
-        *dst = best;
+        // a destination with more than D in-edges owns 2^span adjacent lanes of the batch: minimum over the group
+        const unsigned span = (cur[0] >> 17) & 7u;
+        if (__any_sync(0xffffffffu, span != 0u)) {   // warp-uniform
+#pragma unroll
+            for (int st = 0; st < 5; ++st) {
+                const double other = __shfl_xor_sync(0xffffffffu, best, 1 << st);
+                if (st < (int)span) best = other < best ? other : best;
+            }
+        }
+        if (((threadIdx.x & 31) & ((1u << span) - 1u)) == 0u) *dst = best;
 #pragma unroll
         for (int i = 0; i <= D; ++i) cur[i] = nxt[i];
     }

@@ -135,9 +135,12 @@ Plan make_plan(int N, int E, const int32_t *in_ptr, const int32_t *in_src, int s
 //   down stream (shared by all origins): batches of 1 + D rows - a header row (destination slot per lane;
 //   bit 16: a partial slot, which starts from +inf instead of its old content) and exactly D edge rows
 //   "tail slot | weight position << 16" (padding: +inf slot | zero-weight position).  A warp barrier
-//   precedes every batch.  Destinations with more than D in-edges are split: chunks of D edges go to partial
-//   slots first, the node then combines its partials through zero-weight entries one stage later (again in
-//   chunks of D if need be).  D is chosen per network by the row count of the whole sweep.
+//   precedes every batch.  Destinations with more than D in-edges are split into chunks of D edges over 2^span
+//   adjacent lanes of the same batch (header bits 17-19 = span <= 5): the kernel reduces the group's candidates by
+//   shuffles, its first lane writes - one batch whatever the in-degree up to 32 D (the dense top of the hierarchy has
+//   nodes with dozens of in-edges; as partial slots combined stage by stage they cost two to three batches each).
+//   Beyond 32 D, chunks go to partial slots first and the node combines them one stage later.  D is chosen per
+//   network by the cost model of build_tables.
 //   up stream (one per origin): pairs of rows - the pushing node (same word in every lane), then up to 32
 //   of its edges to higher ranks "head | up-region position << 16" (padding: +inf slot | the +inf weight).
 //   select stream (shared): for every block of 32 nodes SD rows "tail | CSC slot << 16" of their original
@@ -149,7 +152,9 @@ struct DownLayout {
     int batches = 0, D = 0;
 };
 
-struct Item { int level, stage, dest; std::vector<std::pair<int, int>> in; };   // in: (tail slot, edge id or -1 = zero weight)
+// in: (tail slot, edge id or -1 = zero weight).  An item with more than D in-edges takes 2^span ADJACENT lanes of a batch
+// (chunks of D edges per lane); the kernel min-reduces the lanes of the group by shuffles and the first lane writes.
+struct Item { int level, stage, dest, span; std::vector<std::pair<int, int>> in; };
 
 // Layout of the down sweep for edge rows per batch D (see above).
 DownLayout down_layout(const Plan &P, int D)
@@ -178,10 +183,10 @@ DownLayout down_layout(const Plan &P, int D)
         for (int e : dn[v]) in.push_back({P.edges[e].first, e});
         int stage = 0;
         int &ns = next_slot.emplace(level[v], N + 1).first->second;
-        while ((int)in.size() > D) {
+        while ((int)in.size() > 32 * D) {   // wider than a whole batch: partial slots, combined one stage later
             std::vector<std::pair<int, int>> up;
             for (size_t i = 0; i < in.size(); i += D) {
-                Item part{level[v], stage, ns, {}};
+                Item part{level[v], stage, ns, 0, {}};
                 part.in.assign(in.begin() + i, in.begin() + std::min(in.size(), i + D));
                 up.push_back({ns++, -1});
                 items.push_back(std::move(part));
@@ -190,30 +195,43 @@ DownLayout down_layout(const Plan &P, int D)
             ++stage;
         }
         max_slot = std::max(max_slot, ns);
-        items.push_back(Item{level[v], stage, v, std::move(in)});
+        int span = 0;
+        while ((D << span) < (int)in.size()) ++span;
+        items.push_back(Item{level[v], stage, v, span, std::move(in)});
     }
     L.slots = max_slot;
     const uint32_t ZERO = (uint32_t)n_down;   // zero-weight position: padding and partial-combine entries
     L.wlen = n_down + 1;
     int next_pos = 0;
     std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) {
-        return a.level != b.level ? a.level < b.level : a.stage < b.stage;
+        if (a.level != b.level) return a.level < b.level;
+        if (a.stage != b.stage) return a.stage < b.stage;
+        return a.span > b.span;   // widest groups first: every group then starts at a multiple of its width
     });
     const uint32_t pad = (uint32_t)N | (ZERO << 16);   // tail = the +inf slot, weight 0
     for (size_t i = 0; i < items.size();) {
+        // one batch: items of one (level, stage) while their lane groups fit
+        const size_t hdr = L.rows.size();
+        L.rows.resize(hdr + 32, (uint32_t)N);   // idle lane: min(+inf, +inf + 0) back into the +inf slot
+        L.rows.resize(hdr + 32 + (size_t)D * 32, pad);
+        const size_t base = hdr + 32;
+        int lane = 0;
         size_t j = i;
-        while (j < items.size() && j - i < 32 && items[j].level == items[i].level && items[j].stage == items[i].stage) ++j;
-        for (int l = 0; l < 32; ++l)   // idle lane: min(+inf, +inf + 0) back into the +inf slot
-            L.rows.push_back(i + l < j ? (uint32_t)items[i + l].dest | (items[i + l].dest > N ? 0x10000u : 0u) : (uint32_t)N);
-        const size_t base = L.rows.size();
-        L.rows.resize(base + (size_t)D * 32, pad);
-        for (int l = 0; l < 32 && i + l < j; ++l) {
-            const Item &it = items[i + l];
-            for (int t = 0; t < (int)it.in.size(); ++t) {
-                uint32_t wp = ZERO;
-                if (it.in[t].second >= 0) wp = (uint32_t)(L.edge_pos[it.in[t].second] = next_pos++);
-                L.rows[base + (size_t)t * 32 + l] = (uint32_t)it.in[t].first | (wp << 16);
+        for (; j < items.size() && items[j].level == items[i].level && items[j].stage == items[i].stage; ++j) {
+            const Item &it = items[j];
+            const int width = 1 << it.span;
+            if (lane + width > 32) break;
+            for (int c = 0; c < width; ++c) {
+                L.rows[hdr + lane + c] = (uint32_t)it.dest | (it.dest > N ? 0x10000u : 0u) | ((uint32_t)it.span << 17);
+                for (int t = 0; t < D; ++t) {
+                    const size_t k = (size_t)c * D + t;
+                    if (k >= it.in.size()) break;
+                    uint32_t wp = ZERO;
+                    if (it.in[k].second >= 0) wp = (uint32_t)(L.edge_pos[it.in[k].second] = next_pos++);
+                    L.rows[base + (size_t)t * 32 + lane + c] = (uint32_t)it.in[k].first | (wp << 16);
+                }
             }
+            lane += width;
         }
         ++L.batches;
         i = j;
@@ -452,7 +470,13 @@ extern "C" int b200_cch_host_sssp(int N, int E, const int32_t *row, const int32_
                 if (c < best[l]) best[l] = c;
             }
         }
-        for (int l = 0; l < 32; ++l) d[row[l] & 0xffffu] = best[l];
+        for (int l = 0; l < 32; ++l) {   // lane groups: the first lane writes the minimum of the group
+            const int width = 1 << ((row[l] >> 17) & 7u);
+            if (l % width) continue;
+            double m = best[l];
+            for (int c = 1; c < width; ++c) m = std::min(m, best[l + c]);
+            d[row[l] & 0xffffu] = m;
+        }
     }
     for (int v = 0; v < N; ++v) dist_out[v] = d[v];
     if (stats) {
