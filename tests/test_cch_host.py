@@ -79,3 +79,29 @@ def test_hierarchy_on_random_digraphs_with_one_way_links(b200env, native_lib):
         for o in range(n):
             dist, _ = _host_sssp(native_lib, orc, cost, o)
             assert np.array_equal(dist, ref[o]), (seed, o)
+
+
+@pytest.mark.parametrize("force_d", ["2", "3", "8"])
+def test_hierarchy_dense_graph_wide_destinations(b200env, native_lib, monkeypatch, force_d):
+    """A dense digraph: the first eliminated nodes have ~100 higher-ranked in-neighbours.  With D forced to 2 that is
+    more than the 32 x D edges a lane group of one batch can take (partial slots + a second stage), with D = 3 / 8 it
+    is a group of 32 / 16 lanes reduced inside one batch; every variant must reproduce Dijkstra bit for bit."""
+    from oracle.c_oracle import COracle
+    E = b200env.EdgeData
+    n = 110
+    rng = np.random.default_rng(5)
+    links = sorted({(int(a), int(b)) for a, b in rng.integers(1, n + 1, size=(9000, 2)) if a != b})
+    g = b200env.GraphData(num_nodes=n, edges=[E(u, v, 900.0, float(1 + (u * 13 + v * 7) % 9), float(1 + (u * 13 + v * 7) % 9), 0.15, 4.0)
+                                               for u, v in links], od_demand={(1, 2): 1.0})
+    orc = COracle.from_graph_data(g)
+    cost = orc.t0.astype(np.float64)
+    cost[rng.choice(orc.E, orc.E // 4, replace=False)] = 1e6
+    monkeypatch.setenv("B200_CCH_D", force_d)
+    origins = np.array([0, 57, n - 1], dtype=np.int32)   # every call plans the hierarchy again: keep it to three
+    ref, _, _ = orc.sssp(cost, origins)
+    for i, o in enumerate(origins):
+        dist, stats = _host_sssp(native_lib, orc, cost, o)
+        assert np.array_equal(dist, ref[i]), (force_d, o)
+    assert stats[7] == int(force_d)
+    if force_d == "2":
+        assert stats[4] > n + 1, "expected partial slots: in-degree beyond 32 x D"
