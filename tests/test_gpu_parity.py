@@ -804,3 +804,34 @@ def test_general_kernel_hierarchy_on_a_network_with_dead_ends(b200env, native_li
     for s in range(6):
         o = orc.assign(masks[s], None, 10, "msa", penalty=1e4)
         assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"] and a["unassigned"][s] == o["unassigned"]
+
+
+@pytest.mark.parametrize("force_d", ["2", "4"])
+def test_general_kernel_dense_network_wide_lane_groups(b200env, native_lib, monkeypatch, force_d):
+    """A dense 90-node digraph: the hierarchy's first nodes have ~85 higher-ranked in-neighbours, so the down sweep
+    runs lane groups of 32 lanes (D = 4) or goes through partial slots first (D = 2: more than 32 x D in-edges).
+    Flows, TSTT and unassigned demand must equal label correcting and the C oracle bit for bit."""
+    from oracle.c_oracle import COracle
+    E = b200env.EdgeData
+    n = 90
+    rng = np.random.default_rng(6)
+    links = sorted({(int(a), int(b)) for a, b in rng.integers(1, n + 1, size=(7000, 2)) if a != b})
+    g = b200env.GraphData(num_nodes=n, edges=[E(u, v, 900.0, float(1 + (u * 13 + v * 7) % 9), float(1 + (u * 13 + v * 7) % 9), 0.15, 4.0)
+                                               for u, v in links],
+                          od_demand={(int(o), int(d)): float(10 * (1 + (o + d) % 4)) for o in (1, 8, 23, 47, 90)
+                                     for d in (2, 17, 33, 52, 77) if o != d})
+    orc = COracle.from_graph_data(g)
+    masks = _damage_batch(len(links), 5, seed=9, ratio=0.3)
+    monkeypatch.setenv("B200_CCH_D", force_d)
+    cch = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_CCH_D")
+    monkeypatch.setenv("B200_NO_CCH", "1")
+    lc = _engine(b200env, g, "fp32")
+    monkeypatch.delenv("B200_NO_CCH")
+    a, b = _assign(cch, masks, 6, "fw"), _assign(lc, masks, 6, "fw")
+    assert cch.kernel_name == "assign_fused_kernel" and cch.last_config["cch"] == 1 and lc.last_config["cch"] == 0
+    for key in ("flow", "tstt", "unassigned", "status"):
+        assert np.array_equal(a[key], b[key]), key
+    for s in range(5):
+        o = orc.assign(masks[s], None, 6, "fw")
+        assert np.array_equal(a["flow"][s], o["flow"]) and a["tstt"][s] == o["tstt"], s
